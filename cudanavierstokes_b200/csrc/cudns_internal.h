@@ -1,0 +1,90 @@
+// Internal declarations of libcudns (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/cudns.h"
+
+namespace cudns {
+
+constexpr int GX = 4;            // x ghost width in memory (>= s, even: keeps interior rows 16B aligned)
+constexpr int MAXS = 4;
+
+// quantities staged on chip by the RHS kernel
+enum { QR = 0, QU, QV, QW, QH, QP, QT, QM, QD, NQ };
+
+// Padded ghost-cell layout of one field: [pz][py][px], x fastest.
+struct Layout {
+    int mx, my, mz;              // local interior extents (mz = this rank's slab)
+    int gy, gz;                  // ghost widths: gy = s, gz = s + v
+    int px, py, pz;              // padded extents
+    size_t plane, vol;           // px*py, plane*pz
+    __host__ __device__ inline size_t idx(int i, int j, int k) const {
+        return (size_t)(k + gz) * plane + (size_t)(j + gy) * px + (size_t)(i + GX);
+    }
+};
+
+// Everything a kernel needs besides field pointers; passed by value (lives in the constant bank).
+struct KConst {
+    Layout L;
+    int s, v;
+    int kstart;                  // global index of local plane 0 (perturbation strip, sponge)
+    int mz_tot;
+    double d1[3], d2[3];         // 1/Delta, 1/Delta^2 per direction (d_dx.. d_d2z, cuda_utils.cu:61-63,88-90)
+    double aF[MAXS + 1];         // advective first-derivative weights a_l, l=1..s ( = -coeffF[s-l], globals.h:69-82)
+    double aV[MAXS + 1];         // viscous   first-derivative weights
+    double bV[MAXS + 1];         // viscous second-derivative weights b_0..b_v ( = coeffVS[v-l] )
+    double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
+    int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
+    int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
+    double TwallTop, TwallBot;
+    // perturbation.h
+    int kC, LP; double amp1, amp2, omega1, omega2, lambdaP;
+    double Lx, Ly, Lz, CFL;
+    const double *xp;            // [mx]  1/x'(xi)           (device)
+    const double *cVSx;          // [(2v+1)*mx] non-uniform second-derivative table (device)
+    const double *dxv;           // [mx] cell widths          (device)
+    const double *spongeX, *spongeZ, *sref;   // [mx], [mz], [5][mx*mz]
+    const double *dt, *dpdz, *time_on_gpu;    // device scalars
+};
+
+// One Runge-Kutta stage as a generic register update (see DESIGN.md "RK algebra"):
+//   K      = RHS(Q_in)
+//   Q_out  = Q_base + dt*( cN*K + cA*RA + cB*RB )        (conservative; stored primitive)
+//   RW     = wOld*RW + wNew*K                             (skipped when RW == nullptr)
+struct StageCoef {
+    double cN, cA, cB, wOld, wNew;
+};
+
+struct StagePtrs {
+    const double *qin;           // 5 padded fields, stride L.vol
+    const double *qbase;         // 5 padded fields (may equal qin)
+    double *qout;                // 5 padded fields
+    const double *theta;         // padded
+    const double *RA, *RB;       // 5 unpadded fields each (stride N) or nullptr
+    double *RW;                  // 5 unpadded fields or nullptr
+    double *rhs_out;             // test path: write K only (5 unpadded) and skip the update
+    double *viscmax;             // optional: atomic max of mu-based dt limiter (stale-mu semantics)
+};
+
+void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st);
+void launch_rhs_stage(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st);
+void launch_fill_xy(const KConst &kc, double *q5, int nfields, cudaStream_t st);
+void launch_zwrap(const KConst &kc, double *q5, int nfields, cudaStream_t st);
+void launch_pack_z(const KConst &kc, const double *q5, double *send_lo, double *send_hi, cudaStream_t st);
+void launch_unpack_z(const KConst &kc, double *q5, const double *recv_lo, const double *recv_hi, cudaStream_t st);
+void launch_pad(const KConst &kc, const double *src5[5], double *q5, cudaStream_t st);
+void launch_unpad(const KConst &kc, const double *q5, double *dst5[5], cudaStream_t st);
+// reductions: out[0] = max_p conv limiter, out[1] = max_p visc limiter (uses fresh mu), out[2..] sums
+void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st);
+void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st);
+void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
+
+int rhs_stage_smem_bytes(int s);
+bool rhs_stage_supported(int s, int v);
+
+void set_error(const std::string &msg);
+
+}  // namespace cudns

@@ -1,0 +1,179 @@
+/*
+ * cudns.h -- C ABI of libcudns: a B200-native (sm_100a) replacement for the GPU side of
+ * CUDA-DNS (simone-silvestri/CudaNavierStokes): right-hand-side evaluation + Runge-Kutta
+ * time advance of the 3-D compressible Navier-Stokes equations, with halo exchange.
+ *
+ * The reference has no FFI; its seam is the set of free functions that src/main.cpp calls
+ * into the .cu files (src/main.h:23-42) plus host globals (src/globals.h:97-105).  Every entry
+ * point below names the reference function(s) it replaces (paths relative to the reference
+ * repository).  Plain pointers and sizes only; all device memory is owned by the library, all
+ * host arrays by the caller.  Every function returns 0 on success or a CUDNS_E* code;
+ * cudns_last_error() returns a human-readable message for the calling thread.
+ *
+ * Array layout (host side, identical to the reference, src/globals.h:60): x fastest,
+ * index = i + j*mx + k*mx*my; for a multi-rank run each rank passes its own z-slab
+ * [mz_local][my][mx].  State = (r,u,v,w,e) = (rho, u, v, w, rho*E): PRIMITIVE velocities.
+ */
+#ifndef CUDNS_H_
+#define CUDNS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUDNS_OK          0
+#define CUDNS_EINVAL      1   /* bad parameter (reference: printf + exit(1), cuda_utils.cu:55-58,233-297) */
+#define CUDNS_ECUDA       2   /* CUDA runtime/driver error (reference: silently ignored, cuda_globals.h:12-22) */
+#define CUDNS_ENOMEM      3
+#define CUDNS_ESTATE      4   /* call order violation (e.g. advance before set_state) */
+#define CUDNS_EUNSUPPORTED 5
+
+/* Every knob of src/globals.h:14-58, src/sponge.h:5-17 and src/perturbation.h:14-21, as runtime
+ * values (the reference fixes them at compile time).  stencilSize/stencilVisc select pre-built
+ * kernel instantiations. */
+typedef struct cudns_params {
+    int mx, my, mz;            /* GLOBAL grid mx_tot,my_tot,mz_tot                    globals.h:23-25 */
+    int stencilSize;           /* advective half-width s in {1,2,3,4} (order 2s)      globals.h:17 */
+    int stencilVisc;           /* viscous half-width  v <= s                          globals.h:18 */
+    double Lx, Ly, Lz;         /*                                                     globals.h:20-22 */
+    double CFL;                /* globals.h:28 (float literal there: pass (double)(float)value) */
+    int lowStorage;            /* 1 Wray low-storage RK3, 0 Kutta RK3                 globals.h:31 */
+    int boundaryLayer;         /*                                                     globals.h:32 */
+    int perturbed;             /* wall blowing/suction strip                          globals.h:33 */
+    int forcing;               /* body force dpdz + controller                        globals.h:34 */
+    int periodicX;             /*                                                     globals.h:35 */
+    int nonUniformX;           /*                                                     globals.h:36 */
+    int checkCFLcondition;     /* dt (and dpdz) refresh cadence in steps              globals.h:38 */
+    int checkBulk;             /* bulk diagnostics cadence                            globals.h:39 */
+    double Re, Pr, Ma, viscexp, gam;   /*                                             globals.h:41-45 */
+    double stretch;            /*                                                     globals.h:50 */
+    double TwallTop, TwallBot; /*                                                     globals.h:51-52 */
+    double spTopStr, spTopLen, spTopExp;   /* sponge.h:5-7  */
+    double spInlStr, spInlLen, spInlExp;   /* sponge.h:10-12 */
+    double spOutStr, spOutLen, spOutExp;   /* sponge.h:15-17 */
+    int    kC, LP;                          /* perturbation.h:16-17 */
+    double amp1, amp2, omega1, omega2;      /* perturbation.h:19-21 (lambda = Ly/2pi is derived) */
+    int quirk_q1;              /* 1: replicate src/cuda_rhs.cu:175 (y-dissipation uses dvdz); 0: dwdy */
+    int rk4;                   /* 1: classical RK4 (extension; README.md:26 names it, the code lacks it) */
+    /* --- decomposition (replaces pRow/pCol, globals.h:14-15, and Communicator, main.h:10-21):
+     * z-slabs, one rank per GPU; x and y are never split. */
+    int nranks;                /* number of z-slabs (1 = single GPU)                  */
+    int rank;                  /* this process' slab index: k in [rank*mz/nranks, (rank+1)*mz/nranks) */
+    int device;                /* CUDA device ordinal for this rank (setDevice, cuda_utils.cu:815) */
+    int reserved[5];
+} cudns_params;
+
+typedef struct cudns_solver *cudns_handle;
+
+const char *cudns_last_error(void);
+const char *cudns_version(void);
+
+/* presets: python-utils/CompNavierStokes.py:1-7 (Taylor-Green), globals/channel.h, src/globals.h */
+int cudns_params_tgv(cudns_params *p, int n, int stencil);
+int cudns_params_channel(cudns_params *p);
+int cudns_params_blayer(cudns_params *p);
+
+/* ---- host-side set-up helpers (no GPU needed): restate src/init.cpp -------------------- */
+/* initGrid (init.cpp:32-91): x[mx], xp[mx] (=1/x'), xpp[mx], y[my], z[mz]; returns host dx in *dx. */
+int cudns_init_grid(const cudns_params *p, double *x, double *xp, double *xpp, double *y, double *z, double *dx);
+/* initCHIT (init.cpp:126-148) / initChannel (init.cpp:94-124; libc rand(), reference loop order).
+ * Arrays are the GLOBAL field [mz][my][mx]. */
+int cudns_init_chit(const cudns_params *p, const double *x, const double *y, const double *z,
+                    double *r, double *u, double *v, double *w, double *e);
+int cudns_init_channel(const cudns_params *p, const double *x, const double *y, const double *z,
+                       double *r, double *u, double *v, double *w, double *e);
+/* calculateSponge, host half (sponge.cu:83-195): sponge strengths + conservative reference state from
+ * the Blasius profile arrays (blasius1D/{x,r,u,w,e}Prof.bin, n entries each), with a correct 0-based
+ * natural spline.  sigma_x[mx], sigma_z[mz], ref[5][mx*mz] (index i + k*mx); if r..e are non-NULL the
+ * initial field (restartFile<0 branch) is written too. */
+int cudns_build_sponge(const cudns_params *p, const double *x, const double *z,
+                       const double *xIn, const double *rIn, const double *uIn, const double *wIn, int n,
+                       double *sigma_x, double *sigma_z, double *ref5,
+                       double *r, double *u, double *v, double *w, double *e);
+/* writeField / initField (init.cpp:13-30 -> comm.cpp:205-279): fields/<c>.<%07d>.bin, raw float64,
+ * [mz_tot][my_tot][mx_tot], no header.  dir is the directory that contains "fields". */
+int cudns_write_field(const char *dir, char name, int timestep, const double *var, size_t count);
+int cudns_read_field(const char *dir, char name, int timestep, double *var, size_t count);
+
+/* ---- solver life cycle ----------------------------------------------------------------- */
+/* setDevice + setGPUParameters + initSolver (cuda_utils.cu:815,49-179,415-519).  x,xp,xpp are the
+ * arrays of cudns_init_grid (the caller may substitute its own metric tables). */
+int cudns_create(const cudns_params *p, const double *x, const double *xp, const double *xpp, cudns_handle *out);
+/* clearSolver (cuda_utils.cu:521-595) */
+int cudns_destroy(cudns_handle h);
+/* checkGpuMem (cuda_utils.cu:780-813): bytes held by this solver / free / total on its device */
+int cudns_memory_report(cudns_handle h, size_t *solver_bytes, size_t *free_bytes, size_t *total_bytes);
+
+/* copyField(0) (cuda_utils.cu:299-333): host slab -> device, ghost fill, time_on_GPU = 0 and the
+ * first calcState.  copyField(1) (:334-355): device -> host slab. */
+int cudns_set_state(cudns_handle h, const double *r, const double *u, const double *v, const double *w, const double *e);
+int cudns_get_state(cudns_handle h, double *r, double *u, double *v, double *w, double *e);
+/* same, but the five arrays already live on this solver's device (contiguous [mz_local][my][mx]) */
+int cudns_set_state_device(cudns_handle h, const double *d_r, const double *d_u, const double *d_v, const double *d_w, const double *d_e);
+int cudns_get_state_device(cudns_handle h, double *d_r, double *d_u, double *d_v, double *d_w, double *d_e);
+/* copySpongeToDevice (sponge.cu:43-81): sigma_x[mx], sigma_z[mz_local], ref5 = 5 tables [mx*mz_local] */
+int cudns_set_sponge(cudns_handle h, const double *sigma_x, const double *sigma_z, const double *ref5);
+
+/* runSimulationLowStorage / runSimulation (cuda_main.cu:44-186) = one "file" of solverWrapper
+ * (cuda_main.cu:267-327): advance nsteps steps entirely on the device.  time/par1/par2 are host
+ * arrays of nsteps entries or NULL (par1/par2 only written where istep % checkBulk == 0, like the
+ * reference; other entries untouched).  The istep cadence restarts at 0 on every call (quirk Q11). */
+int cudns_advance(cudns_handle h, int nsteps, double *time, double *par1, double *par2);
+
+/* calcRHS (cuda_main.cu:15-42): full right-hand side of (rho, rho u, rho v, rho w, rho E) at the
+ * current state into five host slabs (test entry point; the product path never materialises it). */
+int cudns_calc_rhs(cudns_handle h, double *rhs_r, double *rhs_u, double *rhs_v, double *rhs_w, double *rhs_e);
+/* calcTimeStep (calc_stress.cu:122-160) + allReduceToMin (comm.cpp:294) */
+int cudns_calc_dt(cudns_handle h, double *dt);
+/* calcBulk (calc_stress.cu:162-201) + allReduceSum (comm.cpp:326) */
+int cudns_calc_bulk(cudns_handle h, double *par1, double *par2);
+/* device scalars dtC, dpdz (cuda_utils.cu:65-75), accumulated time (cuda_main.cu:117-119) */
+int cudns_get_scalars(cudns_handle h, double *dt, double *dpdz, double *time);
+/* fix dt (tests): fixed != 0 disables the CFL refresh inside cudns_advance */
+int cudns_set_dt(cudns_handle h, double dt, int fixed);
+
+/* ---- multi-GPU halo plumbing (replaces updateHalo[Five] comm.cpp:90-134 and
+ *      fillBoundaries[Five] cuda_utils.cu:597-778) ------------------------------------------
+ * z-slab neighbours exchange (s+v) full padded planes of the 5 state fields once per RK stage.
+ * Two transports:
+ *  (a) peer memory: each rank publishes a CUDA IPC handle of its state allocation; after
+ *      cudns_halo_connect() the stage kernels' epilogue copies boundary planes straight into the
+ *      neighbour's ghost planes over NVLink and signals with device-side flags;
+ *  (b) external: the caller moves the bytes (e.g. NCCL send/recv on views of the buffers returned
+ *      by cudns_halo_buffers) between cudns_stage_begin/cudns_stage_end.
+ * Scalar reductions (dt: MIN, bulk/forcing: SUM) are delegated to a caller-provided callback so the
+ * library does not link an MPI or NCCL of its own. */
+#define CUDNS_IPC_HANDLE_BYTES 64
+typedef struct cudns_peer_info {
+    unsigned char mem_handle[CUDNS_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the halo mailbox */
+    int device;
+    int pid;
+} cudns_peer_info;
+int cudns_halo_local_info(cudns_handle h, cudns_peer_info *mine);
+/* lower = rank-1 (periodic), upper = rank+1 (periodic) */
+int cudns_halo_connect(cudns_handle h, const cudns_peer_info *lower, const cudns_peer_info *upper);
+/* device pointers + byte counts of the contiguous send/recv plane blocks (transport (b)):
+ * send_lo/send_hi are the first/last (s+v) interior planes (packed 5 fields), recv_lo/recv_hi the
+ * ghost blocks. */
+int cudns_halo_buffers(cudns_handle h, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, size_t *bytes_each);
+typedef void (*cudns_allreduce_fn)(void *user, double *vals, int n, int op /*0 min, 1 sum, 2 max*/);
+int cudns_set_allreduce(cudns_handle h, cudns_allreduce_fn fn, void *user);
+typedef void (*cudns_exchange_fn)(void *user, void *stream /* cudaStream_t */);
+/* transport (b): called once per RK stage (and once in set_state) on the solver's stream after the
+ * send blocks are packed; must enqueue the exchange on that stream (or synchronise itself). */
+int cudns_set_exchange(cudns_handle h, cudns_exchange_fn fn, void *user);
+/* the CUDA stream the solver launches on (cudaStream_t), for event timing by the caller */
+int cudns_get_stream(cudns_handle h, void **stream);
+
+/* counters: kernels launched by this solver since creation / algorithmic bytes moved */
+int cudns_get_counters(cudns_handle h, uint64_t *kernel_launches, uint64_t *rk_stages);
+/* per-kernel device time of the last cudns_profile_stage() call, in ms: theta, rhs_stage, halo */
+int cudns_profile_stage(cudns_handle h, int reps, float *ms_theta, float *ms_rhs, float *ms_halo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUDNS_H_ */
