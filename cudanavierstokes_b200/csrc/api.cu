@@ -1,0 +1,506 @@
+// libcudns C ABI: solver life cycle, time loop, halo plumbing.  See include/cudns.h for the mapping of
+// every entry point onto the reference's functions.
+#include "cudns_internal.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <unistd.h>
+
+namespace cudns {
+const double *coeff_first(int s);
+const double *coeff_second(int s);
+int check_params(const cudns_params *p);
+void launch_dt_combine(double *dt, const double *conv, const double *visc, double cfl, cudaStream_t st);
+}
+using namespace cudns;
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(err__));                        \
+            return CUDNS_ECUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+// device scalar slots
+enum { SC_DT = 0, SC_DPDZ, SC_TGPU, SC_TIME, SC_RED0, SC_RED1, SC_STALE0, SC_STALE1, SC_BULK0, SC_BULK1, SC_BULK2, SC_BULK3, SC_N = 16 };
+
+struct cudns_solver {
+    cudns_params P;
+    KConst kc;
+    Layout L;
+    size_t N;                    // local interior points
+    cudaStream_t st;
+    double *state[3];            // padded 5-field buffers
+    int nstate, cur;
+    double *theta;
+    double *R1, *R2;
+    double *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
+    double *d_scal;
+    double *d_hist; int hist_cap;
+    double *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
+    bool have_state, fixed_dt, have_sponge;
+    cudns_allreduce_fn allreduce; void *allreduce_user;
+    cudns_exchange_fn exchange; void *exchange_user;
+    uint64_t launches, stages;
+    size_t bytes;
+};
+
+static int dmalloc(cudns_solver *S, double **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(double));
+    if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return CUDNS_ENOMEM; }
+    S->bytes += n * sizeof(double);
+    return CUDNS_OK;
+}
+
+extern "C" {
+
+int cudns_create(const cudns_params *p, const double *x, const double *xp, const double *xpp, cudns_handle *out) {
+    int rc = check_params(p); if (rc) return rc;
+    if (!out || !x || !xp || !xpp) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!rhs_stage_supported(p->stencilSize, p->stencilVisc)) { set_error("unsupported stencil"); return CUDNS_EUNSUPPORTED; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: libcudns has no CPU fallback"); return CUDNS_ECUDA; }
+    CK(cudaSetDevice(p->device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, p->device));
+    if (prop.major < 10) { set_error("libcudns is built for sm_100a (B200) only"); return CUDNS_EUNSUPPORTED; }
+    cudns_solver *S = new cudns_solver();
+    std::memset(S, 0, sizeof(*S));
+    S->P = *p;
+    const int s = p->stencilSize, v = p->stencilVisc, mx = p->mx, my = p->my, mzl = p->mz / p->nranks;
+    if (!p->periodicX) {
+        int rem = mx % 32;
+        if (rem != 0 && rem < s + 1) { set_error("non-periodic x: mx % 32 must be 0 or > stencilSize"); delete S; return CUDNS_EINVAL; }
+    }
+    Layout &L = S->L;
+    L.mx = mx; L.my = my; L.mz = mzl; L.gy = s; L.gz = s + v;
+    L.px = ((mx + 2 * GX + 15) / 16) * 16; L.py = my + 2 * s; L.pz = mzl + 2 * L.gz;
+    L.plane = (size_t)L.px * L.py; L.vol = L.plane * L.pz;
+    S->N = (size_t)mx * my * mzl;
+    CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+    S->nstate = (p->lowStorage && !p->rk4) ? 2 : 3;
+    for (int b = 0; b < S->nstate; b++) {
+        if ((rc = dmalloc(S, &S->state[b], 5 * L.vol))) { cudns_destroy(S); return rc; }
+        CK(cudaMemsetAsync(S->state[b], 0, 5 * L.vol * sizeof(double), S->st));
+    }
+    if ((rc = dmalloc(S, &S->theta, L.vol))) { cudns_destroy(S); return rc; }
+    CK(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
+    if ((rc = dmalloc(S, &S->R1, 5 * S->N))) { cudns_destroy(S); return rc; }
+    CK(cudaMemsetAsync(S->R1, 0, 5 * S->N * sizeof(double), S->st));
+    if (!(p->lowStorage && !p->rk4)) { if ((rc = dmalloc(S, &S->R2, 5 * S->N))) { cudns_destroy(S); return rc; } }
+    if ((rc = dmalloc(S, &S->d_xp, mx)) || (rc = dmalloc(S, &S->d_dxv, mx)) || (rc = dmalloc(S, &S->d_cVSx, (size_t)mx * (2 * v + 1))) ||
+        (rc = dmalloc(S, &S->d_scal, SC_N)) || (rc = dmalloc(S, &S->d_spx, mx)) || (rc = dmalloc(S, &S->d_spz, mzl)) ||
+        (rc = dmalloc(S, &S->d_sref, 5 * (size_t)mx * mzl))) { cudns_destroy(S); return rc; }
+    S->halo_doubles = 5 * (size_t)L.gz * L.plane;
+    if (p->nranks > 1) {
+        if ((rc = dmalloc(S, &S->send_lo, S->halo_doubles)) || (rc = dmalloc(S, &S->send_hi, S->halo_doubles)) ||
+            (rc = dmalloc(S, &S->recv_lo, S->halo_doubles)) || (rc = dmalloc(S, &S->recv_hi, S->halo_doubles))) { cudns_destroy(S); return rc; }
+    }
+    // ---- setGPUParameters, cuda_utils.cu:60-139
+    const double *cF = coeff_first(s), *cVF = coeff_first(v), *cVS = coeff_second(v);
+    double dx = p->nonUniformX ? p->Lx * (1.0) / mx : x[1] - x[0];   // host global dx after initGrid (init.cpp:36,63)
+    double Ly_d = p->Ly * (0.5 + 1.0) / my - p->Ly * (0.5) / my;     // y[1]-y[0] exactly as initGrid builds y (init.cpp:67-68)
+    double Lz_d = p->Lz * (0.5 + 1.0) / p->mz - p->Lz * (0.5) / p->mz;
+    double h_dx = 1.0 / dx, h_dy = 1.0 / Ly_d, h_dz = 1.0 / Lz_d;
+    KConst &kc = S->kc;
+    std::memset(&kc, 0, sizeof(kc));
+    kc.L = L; kc.s = s; kc.v = v; kc.kstart = p->rank * mzl; kc.mz_tot = p->mz;
+    kc.d1[0] = h_dx; kc.d1[1] = h_dy; kc.d1[2] = h_dz;
+    kc.d2[0] = h_dx * h_dx; kc.d2[1] = h_dy * h_dy; kc.d2[2] = h_dz * h_dz;
+    for (int l = 1; l <= s; l++) kc.aF[l] = -cF[s - l];
+    for (int l = 1; l <= v; l++) { kc.aV[l] = -cVF[v - l]; kc.bV[l] = cVS[v - l]; }
+    kc.bV[0] = cVS[v];
+    kc.gam = p->gam;
+    kc.Rgas = (1.f / (p->gam * p->Ma * p->Ma));                 // globals.h:48
+    double Ec = ((p->gam - 1.f) * p->Ma * p->Ma);               // globals.h:47
+    kc.cvInv = (p->gam - 1.0) / kc.Rgas;
+    kc.cp = kc.Rgas * p->gam / (p->gam - 1.0);
+    kc.invRe = 1.0 / p->Re; kc.lamfac = 1.0 / p->Pr / Ec; kc.viscexp = p->viscexp;
+    kc.viscmode = p->viscexp == 1.0 ? 1 : p->viscexp == 0.5 ? 2 : p->viscexp == 0.75 ? 3 : p->viscexp == 1.5 ? 4 : 0;
+    kc.periodicX = p->periodicX; kc.boundaryLayer = p->boundaryLayer; kc.nonUniformX = p->nonUniformX;
+    kc.perturbed = p->perturbed; kc.forcing = p->forcing; kc.quirk_q1 = p->quirk_q1;
+    kc.TwallTop = p->TwallTop; kc.TwallBot = p->TwallBot;
+    kc.kC = p->kC; kc.LP = p->LP; kc.amp1 = p->amp1; kc.amp2 = p->amp2; kc.omega1 = p->omega1; kc.omega2 = p->omega2;
+    kc.lambdaP = p->Ly / (2.0 * M_PI);
+    kc.Lx = p->Lx; kc.Ly = p->Ly; kc.Lz = p->Lz; kc.CFL = p->CFL;
+    {
+        std::vector<double> dxv(mx), tab((size_t)mx * (2 * v + 1));
+        dxv[0] = (x[1] + x[0]) / 2.0;
+        for (int i = 1; i < mx - 1; i++) dxv[i] = (x[i + 1] - x[i - 1]) / 2.0;
+        dxv[mx - 1] = p->Lx - (x[mx - 1] + x[mx - 2]) / 2.0;
+        const double h_d2x = h_dx * h_dx;
+        for (int it = 0; it < v; it++)
+            for (int i = 0; i < mx; i++)
+                tab[i + (size_t)it * mx] = (cVS[it] * (xp[i] * xp[i]) * h_d2x - cVF[it] * xpp[i] * (xp[i] * xp[i] * xp[i]) * h_dx);
+        for (int i = 0; i < mx; i++) tab[i + (size_t)v * mx] = cVS[v] * (xp[i] * xp[i]) * h_d2x;
+        for (int it = v + 1; it < 2 * v + 1; it++)
+            for (int i = 0; i < mx; i++)
+                tab[i + (size_t)it * mx] = (cVS[2 * v - it] * (xp[i] * xp[i]) * h_d2x + cVF[2 * v - it] * xpp[i] * (xp[i] * xp[i] * xp[i]) * h_dx);
+        CK(cudaMemcpy(S->d_dxv, dxv.data(), mx * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S->d_cVSx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S->d_xp, xp, mx * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    kc.xp = S->d_xp; kc.cVSx = S->d_cVSx; kc.dxv = S->d_dxv;
+    kc.spongeX = nullptr; kc.spongeZ = nullptr; kc.sref = nullptr;
+    kc.dt = S->d_scal + SC_DT; kc.dpdz = S->d_scal + SC_DPDZ; kc.time_on_gpu = S->d_scal + SC_TGPU;
+    double sc0[SC_N]; std::memset(sc0, 0, sizeof(sc0));
+    sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
+    CK(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
+    // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
+    if ((size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    CK(cudaStreamSynchronize(S->st));
+    *out = S;
+    return CUDNS_OK;
+}
+
+int cudns_destroy(cudns_handle S) {
+    if (!S) return CUDNS_OK;
+    cudaSetDevice(S->P.device);
+    if (S->st) cudaStreamSynchronize(S->st);
+    for (int b = 0; b < 3; b++) cudaFree(S->state[b]);
+    cudaFree(S->theta); cudaFree(S->R1); cudaFree(S->R2);
+    cudaFree(S->d_xp); cudaFree(S->d_cVSx); cudaFree(S->d_dxv); cudaFree(S->d_spx); cudaFree(S->d_spz); cudaFree(S->d_sref);
+    cudaFree(S->d_scal); cudaFree(S->d_hist);
+    cudaFree(S->send_lo); cudaFree(S->send_hi); cudaFree(S->recv_lo); cudaFree(S->recv_hi);
+    if (S->st) cudaStreamDestroy(S->st);
+    delete S;
+    return CUDNS_OK;
+}
+
+int cudns_memory_report(cudns_handle S, size_t *solver_bytes, size_t *free_bytes, size_t *total_bytes) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    size_t f = 0, t = 0; CK(cudaMemGetInfo(&f, &t));
+    if (solver_bytes) *solver_bytes = S->bytes;
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return CUDNS_OK;
+}
+
+int cudns_set_allreduce(cudns_handle S, cudns_allreduce_fn fn, void *user) { if (!S) return CUDNS_EINVAL; S->allreduce = fn; S->allreduce_user = user; return CUDNS_OK; }
+int cudns_set_exchange(cudns_handle S, cudns_exchange_fn fn, void *user) { if (!S) return CUDNS_EINVAL; S->exchange = fn; S->exchange_user = user; return CUDNS_OK; }
+int cudns_get_stream(cudns_handle S, void **stream) { if (!S || !stream) return CUDNS_EINVAL; *stream = (void *)S->st; return CUDNS_OK; }
+int cudns_halo_buffers(cudns_handle S, void **send_lo, void **send_hi, void **recv_lo, void **recv_hi, size_t *bytes_each) {
+    if (!S) return CUDNS_EINVAL;
+    if (send_lo) *send_lo = S->send_lo; if (send_hi) *send_hi = S->send_hi;
+    if (recv_lo) *recv_lo = S->recv_lo; if (recv_hi) *recv_hi = S->recv_hi;
+    if (bytes_each) *bytes_each = S->halo_doubles * sizeof(double);
+    return CUDNS_OK;
+}
+int cudns_halo_local_info(cudns_handle S, cudns_peer_info *mine) {
+    if (!S || !mine) return CUDNS_EINVAL;
+    set_error("peer-memory halo transport is not built yet (round 2); use cudns_set_exchange");
+    return CUDNS_EUNSUPPORTED;
+}
+int cudns_halo_connect(cudns_handle S, const cudns_peer_info *, const cudns_peer_info *) {
+    if (!S) return CUDNS_EINVAL;
+    set_error("peer-memory halo transport is not built yet (round 2); use cudns_set_exchange");
+    return CUDNS_EUNSUPPORTED;
+}
+int cudns_get_counters(cudns_handle S, uint64_t *kernel_launches, uint64_t *rk_stages) {
+    if (!S) return CUDNS_EINVAL;
+    if (kernel_launches) *kernel_launches = S->launches;
+    if (rk_stages) *rk_stages = S->stages;
+    return CUDNS_OK;
+}
+
+}  // extern "C"
+
+// z ghosts of a padded 5-field buffer: periodic wrap on one device, exchange with the slab neighbours otherwise
+static int fill_z_ghosts(cudns_solver *S, double *q) {
+    if (S->P.nranks == 1) {
+        if (!S->P.boundaryLayer) { launch_zwrap(S->kc, q, 5, S->st); S->launches++; }
+        return CUDNS_OK;
+    }
+    if (!S->exchange) { set_error("nranks > 1 needs a halo transport: call cudns_set_exchange (or cudns_halo_connect)"); return CUDNS_ESTATE; }
+    launch_pack_z(S->kc, q, S->send_lo, S->send_hi, S->st);
+    S->exchange(S->exchange_user, (void *)S->st);
+    launch_unpack_z(S->kc, q, S->recv_lo, S->recv_hi, S->st);
+    S->launches += 2;
+    return CUDNS_OK;
+}
+
+static void reduce_across(cudns_solver *S, double *dptr, int n, int op) {
+    if (S->P.nranks > 1 && S->allreduce) S->allreduce(S->allreduce_user, dptr, n, op);
+}
+
+extern "C" {
+
+int cudns_set_state_device(cudns_handle S, const double *d_r, const double *d_u, const double *d_v, const double *d_w, const double *d_e) {
+    if (!S || !d_r || !d_u || !d_v || !d_w || !d_e) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    const double *src[5] = {d_r, d_u, d_v, d_w, d_e};
+    S->cur = 0;
+    launch_pad(S->kc, src, S->state[0], S->st);
+    launch_fill_xy(S->kc, S->state[0], 5, S->st);
+    S->launches += 2;
+    int rc = fill_z_ghosts(S, S->state[0]); if (rc) return rc;
+    // time_on_GPU = 0 (initDevice cuda_utils.cu:385) ; the "first calcState" (:332) only matters through the mu that
+    // the first dt refresh sees: keep its viscous limiter
+    CK(cudaMemsetAsync(S->d_scal + SC_TGPU, 0, sizeof(double), S->st));
+    launch_dt_reduce(S->kc, S->state[0], S->d_scal + SC_RED0, S->st); S->launches++;
+    CK(cudaMemcpyAsync(S->d_scal + SC_STALE0, S->d_scal + SC_RED0, 2 * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+    reduce_across(S, S->d_scal + SC_STALE0, 2, 2);
+    CK(cudaStreamSynchronize(S->st));
+    S->have_state = true;
+    return CUDNS_OK;
+}
+
+int cudns_get_state_device(cudns_handle S, double *d_r, double *d_u, double *d_v, double *d_w, double *d_e) {
+    if (!S || !d_r || !d_u || !d_v || !d_w || !d_e) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    double *dst[5] = {d_r, d_u, d_v, d_w, d_e};
+    launch_unpad(S->kc, S->state[S->cur], dst, S->st); S->launches++;
+    CK(cudaStreamSynchronize(S->st));
+    return CUDNS_OK;
+}
+
+// copyField(0), cuda_utils.cu:317-333
+int cudns_set_state(cudns_handle S, const double *r, const double *u, const double *v, const double *w, const double *e) {
+    if (!S || !r || !u || !v || !w || !e) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    // stage through the register array R1 (5*N doubles), exactly the staging role of d_fr.. in the reference
+    const double *src[5] = {r, u, v, w, e};
+    for (int f = 0; f < 5; f++) CK(cudaMemcpyAsync(S->R1 + f * S->N, src[f], S->N * sizeof(double), cudaMemcpyHostToDevice, S->st));
+    return cudns_set_state_device(S, S->R1, S->R1 + S->N, S->R1 + 2 * S->N, S->R1 + 3 * S->N, S->R1 + 4 * S->N);
+}
+
+// copyField(1), cuda_utils.cu:334-355.  Between steps the register array holds no live data for the
+// low-storage scheme's first stage (alpha_0 = 0) nor for Kutta/RK4, so it doubles as the staging buffer.
+int cudns_get_state(cudns_handle S, double *r, double *u, double *v, double *w, double *e) {
+    if (!S || !r || !u || !v || !w || !e) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    int rc = cudns_get_state_device(S, S->R1, S->R1 + S->N, S->R1 + 2 * S->N, S->R1 + 3 * S->N, S->R1 + 4 * S->N);
+    if (rc) return rc;
+    double *dst[5] = {r, u, v, w, e};
+    for (int f = 0; f < 5; f++) CK(cudaMemcpyAsync(dst[f], S->R1 + f * S->N, S->N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return CUDNS_OK;
+}
+
+int cudns_set_sponge(cudns_handle S, const double *sigma_x, const double *sigma_z, const double *ref5) {
+    if (!S || !sigma_x || !sigma_z || !ref5) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    CK(cudaMemcpy(S->d_spx, sigma_x, S->L.mx * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->d_spz, sigma_z, S->L.mz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S->d_sref, ref5, 5 * (size_t)S->L.mx * S->L.mz * sizeof(double), cudaMemcpyHostToDevice));
+    S->kc.spongeX = S->d_spx; S->kc.spongeZ = S->d_spz; S->kc.sref = S->d_sref;
+    S->have_sponge = true;
+    return CUDNS_OK;
+}
+
+int cudns_set_dt(cudns_handle S, double dt, int fixed) {
+    if (!S) return CUDNS_EINVAL;
+    CK(cudaSetDevice(S->P.device));
+    CK(cudaMemcpy(S->d_scal + SC_DT, &dt, sizeof(double), cudaMemcpyHostToDevice));
+    S->fixed_dt = fixed != 0;
+    return CUDNS_OK;
+}
+
+int cudns_get_scalars(cudns_handle S, double *dt, double *dpdz, double *time) {
+    if (!S) return CUDNS_EINVAL;
+    CK(cudaSetDevice(S->P.device));
+    double h[4];
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(h, S->d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dt) *dt = h[SC_DT]; if (dpdz) *dpdz = h[SC_DPDZ]; if (time) *time = h[SC_TIME];
+    return CUDNS_OK;
+}
+
+}  // extern "C"
+
+// one RHS evaluation + register update: K = RHS(state[in]); see StageCoef
+static int run_stage(cudns_solver *S, int in, int base, int out, const double *RA, const double *RB, double *RW,
+                     const StageCoef &c, double *rhs_out) {
+    launch_theta(S->kc, S->state[in], S->theta, S->st);
+    StagePtrs p;
+    p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
+    p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
+    launch_rhs_stage(S->kc, p, c, S->st);
+    S->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
+    if (!rhs_out) { int rc = fill_z_ghosts(S, S->state[out]); if (rc) return rc; S->stages++; }
+    return CUDNS_OK;
+}
+
+// viscous limiter of the state the LAST calcState saw (the reference refreshes dt with the mu field left by the
+// final stage's calcState, i.e. of the state before that stage's update: cuda_main.cu:171,249-251, calc_stress.cu:131)
+static void record_stale_visc(cudns_solver *S, int in) {
+    launch_dt_reduce(S->kc, S->state[in], S->d_scal + SC_RED0, S->st); S->launches++;
+    cudaMemcpyAsync(S->d_scal + SC_STALE1, S->d_scal + SC_RED1, sizeof(double), cudaMemcpyDeviceToDevice, S->st);
+    reduce_across(S, S->d_scal + SC_STALE1, 1, 2);
+}
+
+extern "C" {
+
+int cudns_calc_rhs(cudns_handle S, double *rhs_r, double *rhs_u, double *rhs_v, double *rhs_w, double *rhs_e) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    double *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, 5 * S->N * sizeof(double)));
+    StageCoef c = {1, 0, 0, 0, 0};
+    int rc = run_stage(S, S->cur, S->cur, S->cur, nullptr, nullptr, nullptr, c, tmp);
+    if (rc) { cudaFree(tmp); return rc; }
+    double *dst[5] = {rhs_r, rhs_u, rhs_v, rhs_w, rhs_e};
+    for (int f = 0; f < 5; f++)
+        if (dst[f]) CK(cudaMemcpyAsync(dst[f], tmp + f * S->N, S->N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    cudaFree(tmp);
+    return CUDNS_OK;
+}
+
+int cudns_calc_dt(cudns_handle S, double *dt) {
+    if (!S || !dt) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    launch_dt_reduce(S->kc, S->state[S->cur], S->d_scal + SC_RED0, S->st); S->launches++;
+    reduce_across(S, S->d_scal + SC_RED0, 2, 2);
+    double h[2];
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(h, S->d_scal + SC_RED0, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    *dt = S->P.CFL / fmax(h[0], h[1]);
+    return CUDNS_OK;
+}
+
+int cudns_calc_bulk(cudns_handle S, double *par1, double *par2) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    launch_bulk_reduce(S->kc, S->state[S->cur], S->d_scal + SC_BULK0, S->st); S->launches++;
+    reduce_across(S, S->d_scal + SC_BULK0, 4, 1);
+    double h[4];
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(h, S->d_scal + SC_BULK0, 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (S->P.forcing) { if (par1) *par1 = h[2] / h[1]; if (par2) *par2 = h[3]; }
+    else { if (par1) *par1 = h[0]; }
+    return CUDNS_OK;
+}
+
+// runSimulationLowStorage / runSimulation, cuda_main.cu:44-186
+int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double *par2) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("cudns_advance before cudns_set_state"); return CUDNS_ESTATE; }
+    if (nsteps < 0) { set_error("nsteps < 0"); return CUDNS_EINVAL; }
+    if (S->P.boundaryLayer && !S->have_sponge) { set_error("boundaryLayer needs cudns_set_sponge first"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    if (nsteps == 0) return CUDNS_OK;
+    if (S->hist_cap < nsteps) {
+        cudaFree(S->d_hist); S->d_hist = nullptr;
+        CK(cudaMalloc((void **)&S->d_hist, 3 * (size_t)nsteps * sizeof(double)));
+        S->hist_cap = nsteps;
+    }
+    CK(cudaMemsetAsync(S->d_hist, 0xff, 3 * (size_t)S->hist_cap * sizeof(double), S->st));   // NaN = "not written"
+    double *h_time = S->d_hist, *h_p1 = S->d_hist + S->hist_cap, *h_p2 = S->d_hist + 2 * S->hist_cap;
+    double *sc = S->d_scal;
+    const cudns_params &P = S->P;
+    const bool ls = P.lowStorage && !P.rk4;
+    for (int istep = 0; istep < nsteps; istep++) {
+        // ---- calcTimeStepPressGrad, cuda_main.cu:249-265
+        if (istep % P.checkCFLcondition == 0) {
+            if (!S->fixed_dt) {
+                launch_dt_reduce(S->kc, S->state[S->cur], sc + SC_RED0, S->st); S->launches++;
+                reduce_across(S, sc + SC_RED0, 1, 2);
+                launch_dt_combine(sc + SC_DT, sc + SC_RED0, sc + SC_STALE1, P.CFL, S->st); S->launches++;
+            }
+            if (P.forcing) {
+                launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->st);
+                reduce_across(S, sc + SC_BULK0, 4, 1);
+                launch_scalar_ops(2, sc + SC_DPDZ, sc + SC_BULK0, nullptr, S->st);
+                S->launches += 2;
+            }
+        }
+        launch_scalar_ops(1, sc + SC_TIME, sc + SC_DT, nullptr, S->st);      // deviceSumOne, cuda_main.cu:117-118
+        launch_scalar_ops(1, sc + SC_TGPU, sc + SC_DT, nullptr, S->st);      // deviceAdvanceTime, calc_stress.cu:12
+        S->launches += 2;
+        CK(cudaMemcpyAsync(h_time + istep, sc + SC_TIME, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+        if (istep % P.checkBulk == 0) {                                       // calcBulk, calc_stress.cu:162-201
+            launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->st); S->launches++;
+            reduce_across(S, sc + SC_BULK0, 4, 1);
+            if (P.forcing) {
+                launch_scalar_ops(3, h_p1 + istep, sc + SC_BULK0, nullptr, S->st); S->launches++;
+                CK(cudaMemcpyAsync(h_p2 + istep, sc + SC_BULK3, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+            } else {
+                CK(cudaMemcpyAsync(h_p1 + istep, sc + SC_BULK0, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+            }
+        }
+        const bool need_stale = !S->fixed_dt && (((istep + 1) % P.checkCFLcondition == 0) || istep == nsteps - 1);
+        int rc = 0;
+        if (ls) {
+            // Wray low-storage RK3, cuda_main.cu:10-11,126-184: q += dt (alpha_s k_{s-1} + beta_s k_s); one register set
+            const int a = S->cur, b = 1 - S->cur;
+            StageCoef c0 = {8. / 15., 0, 0, 0, 1}, c1 = {5. / 12., -17. / 60., 0, 0, 1}, c2 = {3. / 4., -5. / 12., 0, 0, 1};
+            rc = run_stage(S, a, a, b, nullptr, nullptr, S->R1, c0, nullptr); if (rc) return rc;
+            rc = run_stage(S, b, b, a, S->R1, nullptr, S->R1, c1, nullptr); if (rc) return rc;
+            if (need_stale) record_stale_visc(S, a);
+            rc = run_stage(S, a, a, b, S->R1, nullptr, nullptr, c2, nullptr); if (rc) return rc;
+            S->cur = b;
+        } else if (!P.rk4) {
+            // Kutta RK3, cuda_main.cu:57-105: q1 = q0 + dt/2 k1; q2 = q0 + dt(2k2 - k1); q = q0 + dt(k1 + 4k2 + k3)/6
+            const int q0 = S->cur, qa = (S->cur + 1) % 3, qb = (S->cur + 2) % 3;
+            StageCoef c0 = {0.5, 0, 0, 0, 1}, c1 = {2.0, -1.0, 0, 0, 1}, c2 = {1. / 6., 1. / 6., 4. / 6., 0, 0};
+            rc = run_stage(S, q0, q0, qa, nullptr, nullptr, S->R1, c0, nullptr); if (rc) return rc;
+            rc = run_stage(S, qa, q0, qb, S->R1, nullptr, S->R2, c1, nullptr); if (rc) return rc;
+            if (need_stale) record_stale_visc(S, qb);
+            rc = run_stage(S, qb, q0, qa, S->R1, S->R2, nullptr, c2, nullptr); if (rc) return rc;
+            S->cur = qa;
+        } else {
+            // classical RK4 (extension): R1 accumulates k1 + 2k2 + 2k3
+            const int q0 = S->cur, qa = (S->cur + 1) % 3, qb = (S->cur + 2) % 3;
+            StageCoef c0 = {0.5, 0, 0, 0, 1}, c1 = {0.5, 0, 0, 1, 2}, c2 = {1.0, 0, 0, 1, 2}, c3 = {1. / 6., 1. / 6., 0, 0, 0};
+            rc = run_stage(S, q0, q0, qa, nullptr, nullptr, S->R1, c0, nullptr); if (rc) return rc;
+            rc = run_stage(S, qa, q0, qb, nullptr, nullptr, S->R1, c1, nullptr); if (rc) return rc;
+            rc = run_stage(S, qb, q0, qa, nullptr, nullptr, S->R1, c2, nullptr); if (rc) return rc;
+            if (need_stale) record_stale_visc(S, qa);
+            rc = run_stage(S, qa, q0, qb, S->R1, nullptr, nullptr, c3, nullptr); if (rc) return rc;
+            S->cur = qb;
+        }
+    }
+    if (time) CK(cudaMemcpyAsync(time, h_time, nsteps * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(std::string("advance: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
+    if (par1 || par2) {
+        std::vector<double> b1(nsteps), b2(nsteps);
+        CK(cudaMemcpy(b1.data(), h_p1, nsteps * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(b2.data(), h_p2, nsteps * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nsteps; i++) {
+            if (par1 && i % P.checkBulk == 0) par1[i] = b1[i];
+            if (par2 && i % P.checkBulk == 0 && P.forcing) par2[i] = b2[i];
+        }
+    }
+    return CUDNS_OK;
+}
+
+int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs, float *ms_halo) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    if (reps < 1) reps = 1;
+    cudaEvent_t e0, e1, e2, e3;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
+    float t_th = 0, t_rhs = 0, t_h = 0;
+    const int a = S->cur, b = (S->cur + 1) % S->nstate;
+    StageCoef c = {0.0, 0, 0, 0, 1};     // cN = 0: the state is copied through unchanged, so reps do not drift
+    for (int r = 0; r < reps; r++) {
+        CK(cudaEventRecord(e0, S->st));
+        launch_theta(S->kc, S->state[a], S->theta, S->st);
+        CK(cudaEventRecord(e1, S->st));
+        StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
+        p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
+        launch_rhs_stage(S->kc, p, c, S->st);
+        CK(cudaEventRecord(e2, S->st));
+        int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc;
+        CK(cudaEventRecord(e3, S->st));
+        CK(cudaEventSynchronize(e3));
+        float x; cudaEventElapsedTime(&x, e0, e1); t_th += x; cudaEventElapsedTime(&x, e1, e2); t_rhs += x; cudaEventElapsedTime(&x, e2, e3); t_h += x;
+        S->launches += 2;
+    }
+    if (ms_theta) *ms_theta = t_th / reps; if (ms_rhs) *ms_rhs = t_rhs / reps; if (ms_halo) *ms_halo = t_h / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    return CUDNS_OK;
+}
+
+}  // extern "C"

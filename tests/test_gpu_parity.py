@@ -1,0 +1,145 @@
+"""GPU parity tests: libcudns (CUDA, through the C ABI) against the CPU oracle and against the outputs of
+the reference's own GPU binary (tests/golden/ref_*.npz).  FP64 tolerance: 1e-12 relative, max-norm, per
+conserved variable (BASELINE.json north_star / BASELINE.md section 6); where a looser bound is used the
+reason is stated at the assertion."""
+import numpy as np
+import pytest
+
+import cudanavierstokes_b200 as cd
+import oracle_binding as ob
+from common import CONFIGS, apply_cfg, blasius_profiles, conserved, load_golden, make_pair, relerr, smooth_random_state
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _rhs_check(o, s, tol=TOL):
+    a = s.rhs(); b = o.rhs()
+    errs = [relerr(x, y) for x, y in zip(a, b)]
+    assert max(errs) < tol, errs
+
+
+@pytest.mark.parametrize("sv", [(1, 1), (2, 1), (2, 2), (3, 1), (3, 2), (3, 3), (4, 1), (4, 2), (4, 3), (4, 4)])
+def test_rhs_tgv_all_stencils(sv):
+    op = ob.params_tgv(24, sv[0], stencilVisc=sv[1])
+    o, s, grid = make_pair(op)
+    o.init_chit(); s.set_state(o.state())
+    _rhs_check(o, s)
+
+
+@pytest.mark.parametrize("shape", [(40, 20, 24), (24, 36, 16), (70, 10, 12)])
+def test_rhs_random_field_ragged_tiles(shape):
+    """grids that are not multiples of the 32x8 tile, smooth random rho,T,u (rho,T>0)"""
+    op = ob.params_tgv(24, 3, mx=shape[0], my=shape[1], mz=shape[2], Lx=3.0, Ly=5.0, Lz=4.0, viscexp=0.7)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    _rhs_check(o, s)
+
+
+def test_rhs_z_chunk_seams():
+    """tall thin grid: the stage kernel splits z into several chunks (each with its own 2s-plane prologue)"""
+    op = ob.params_tgv(24, 1, mx=32, my=8, mz=64)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    _rhs_check(o, s)
+
+
+def test_rhs_quirk_q1_off():
+    op = ob.params_tgv(24, 3, quirk_q1=0)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    _rhs_check(o, s)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_matches_reference_gpu_binary(name):
+    """start from the reference's own file 0, advance 2 x 10 steps like its two output files, compare with its file 2"""
+    cfg = CONFIGS[name]; g = load_golden(name)
+    op = apply_cfg(ob.params_tgv(24, 3), cfg)
+    cp = apply_cfg(cd.Params(), cfg); cp.gam = 1.4; cp.TwallTop = cp.TwallBot = 1.0; cp.quirk_q1 = 1; cp.nranks = 1
+    for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
+              "kC", "LP", "amp1", "amp2", "omega2"):
+        setattr(cp, k, getattr(op, k))
+    grid = cd.init_grid(cp)
+    s = cd.Solver(cp, grid)
+    if cfg["case"] == "blayer":
+        x, r, u, w, e = blasius_profiles()
+        sx, sz, ref, ic = cd.build_sponge(cp, grid, x[1:], r[1:], u[1:], w[1:])    # quirk Q9: the reference skips the first knot
+        s.set_sponge(sx, sz, ref)
+        for a, b in zip(ic, g["file0"]):
+            assert relerr(a, b, floor=1e-30) < 1e-13 or np.abs(b).max() == 0
+    s.set_state(list(g["file0"]))
+    s.advance(cfg["nsteps"])
+    t, p1, p2 = s.advance(cfg["nsteps"])
+    got = conserved(s.get_state()); ref = conserved(list(g["file2"]))
+    errs = [relerr(a, b) for a, b in zip(got, ref)]
+    # The reference GPU build itself differs from the CPU oracle by up to ~1e-13 (FMA contraction, pow), and the
+    # spanwise momentum of the boundary layer is a 1e-6-sized perturbation response, hence 1e-10 there.
+    lim = [5e-12, 5e-12, 2e-10 if cfg["case"] == "blayer" else 5e-12, 5e-12, 5e-12]
+    assert all(e < l for e, l in zip(errs, lim)), errs
+    sc = s.scalars()
+    assert abs(sc["dt"] - g["dt_dpdz"][-1, 0]) <= 5e-7 * sc["dt"]        # the reference prints 7 significant digits
+    if cfg["forcing"]:
+        assert abs(sc["dpdz"] - g["dt_dpdz"][-1, 1]) <= 5e-7 * abs(sc["dpdz"])
+
+
+@pytest.mark.parametrize("scheme", ["lowstorage", "kutta", "rk4"])
+def test_tgv32_steps_vs_oracle(scheme):
+    op = ob.params_tgv(32, 3, lowStorage=int(scheme == "lowstorage"), rk4=int(scheme == "rk4"))
+    o, s, grid = make_pair(op)
+    o.init_chit(); s.set_state(o.state())
+    for n in (1, 9, 10):          # 1, 10, 20 steps: crosses two dt refreshes
+        t0, a1, a2 = o.run(n); t1, b1, b2 = s.advance(n)
+        errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+        assert max(errs) < TOL, (n, errs)
+        assert abs(s.scalars()["dt"] - o.dt) <= 1e-14 * o.dt
+        np.testing.assert_allclose(t1 - t1[0], t0 - t0[0], rtol=0, atol=1e-13)
+    # Taylor-Green kinetic-energy history par1 = <u.u> (calc_stress.cu:192-196)
+    assert abs(b1[0] - a1[0]) < 1e-13
+
+
+def test_dt_and_bulk():
+    op = ob.params_tgv(24, 3)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    assert abs(s.calc_dt() - o.calc_dt()) <= 1e-15 * o.calc_dt()
+    assert abs(s.bulk()[0] - o.bulk()[0]) <= 1e-13 * abs(o.bulk()[0])
+
+
+def test_channel_forcing_controller_vs_oracle():
+    cfg = CONFIGS["chan_s2v2"]
+    op = apply_cfg(ob.params_tgv(24, 3), cfg)
+    o, s, grid = make_pair(op)
+    o.init_channel(); s.set_state(o.state())
+    t0, a1, a2 = o.run(12); t1, b1, b2 = s.advance(12)
+    errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+    assert max(errs) < TOL, errs
+    assert abs(s.scalars()["dpdz"] - o.dpdz) <= 1e-12 * abs(o.dpdz)
+    for i in (0, 5, 10):
+        assert abs(b1[i] - a1[i]) <= 1e-12 * abs(a1[i]) and abs(b2[i] - a2[i]) <= 1e-12 * abs(a2[i])
+
+
+def test_state_roundtrip_and_errors():
+    op = ob.params_tgv(24, 2)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o)
+    s.set_state(st)
+    for a, b in zip(s.get_state(), st):
+        assert np.array_equal(a, b)          # copyField(0) then copyField(1) is the identity, bit for bit
+    bad = cd.params_tgv(24, 2, stencilVisc=3)
+    with pytest.raises(cd.CudnsError):
+        cd.Solver(bad)
+    fresh = cd.Solver(cd.params_tgv(24, 2))
+    with pytest.raises(cd.CudnsError):
+        fresh.advance(1)                     # advance before set_state
+
+
+def test_conservation_periodic_inviscid_limit():
+    """size-independent property: the split form telescopes, so sum(rhs) of rho, rho u_i vanishes to round-off on a
+    periodic box (and of rho E when mu -> 0)"""
+    op = ob.params_tgv(24, 4, Re=1e30, mx=64, my=32, mz=32)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); s.set_state(st)
+    rhs = s.rhs()
+    for k in range(5):
+        assert abs(rhs[k].sum()) < 1e-9 * np.abs(rhs[k]).sum()
