@@ -243,6 +243,14 @@ class Solver:
         _check(self.L.cudns_get_state(self.h, *[_dp(q) for q in out]))
         return out
 
+    def get_state_into(self, out):
+        """copyField(1) into caller-owned (e.g. pinned) float64 arrays of the slab shape"""
+        for q in out:
+            if q.shape != self.shape or q.dtype != np.float64 or not q.flags["C_CONTIGUOUS"]:
+                raise ValueError("output arrays must be C-contiguous float64 of shape %s" % (self.shape,))
+        _check(self.L.cudns_get_state(self.h, *[_dp(q) for q in out]))
+        return out
+
     def set_state_device(self, ptrs):
         _check(self.L.cudns_set_state_device(self.h, *[C.c_void_p(int(q)) for q in ptrs]))
 
