@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <unistd.h>
 
 namespace cudns {
@@ -45,7 +46,37 @@ struct cudns_solver {
     cudns_exchange_fn exchange; void *exchange_user;
     uint64_t launches, stages;
     size_t bytes;
+    StageMaps maps[3];           // TMA descriptors of state[b] (+ theta)
+    bool legacy_stage;           // CUDNS_STAGE=smem: first-generation shared-memory-ring kernel (A/B timing only)
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcudns does not link libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    }
+    return fn;
+}
+// padded field(s) [nf][pz][py][px] of doubles -> descriptor with box bx x by x 1 (x nf)
+static int make_map(CUtensorMap *m, const Layout &L, double *base, int nf, int bx, int by) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CUDNS_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)L.px, (cuuint64_t)L.py, (cuuint64_t)L.pz, (cuuint64_t)nf};
+    cuuint64_t strides[3] = {(cuuint64_t)L.px * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.vol * 8};
+    cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)nf};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const int rank = nf > 1 ? 4 : 3;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return CUDNS_ECUDA; }
+    return CUDNS_OK;
+}
 
 static int dmalloc(cudns_solver *S, double **p, size_t n) {
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(double));
@@ -111,6 +142,10 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     for (int l = 1; l <= s; l++) kc.aF[l] = -cF[s - l];
     for (int l = 1; l <= v; l++) { kc.aV[l] = -cVF[v - l]; kc.bV[l] = cVS[v - l]; }
     kc.bV[0] = cVS[v];
+    for (int d = 0; d < 3; d++) {
+        for (int l = 1; l <= s; l++) { kc.cC[d][l] = -0.25 * kc.aF[l] * kc.d1[d]; kc.cP[d][l] = kc.aF[l] * kc.d1[d]; }
+        for (int l = 0; l <= v; l++) { kc.c1[d][l] = kc.aV[l] * kc.d1[d]; kc.c2[d][l] = kc.bV[l] * kc.d2[d]; }
+    }
     kc.gam = p->gam;
     kc.Rgas = (1.f / (p->gam * p->Ma * p->Ma));                 // globals.h:48
     double Ec = ((p->gam - 1.f) * p->Ma * p->Ma);               // globals.h:47
@@ -148,7 +183,21 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
     CK(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
-    if ((size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    {
+        const char *env = getenv("CUDNS_STAGE");
+        S->legacy_stage = env && std::string(env) == "smem";
+    }
+    if ((size_t)stage_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin ||
+        (size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
+        const int ty = stage_tile_y(), CXb = 32 + 2 * GX, CYb = ty + 2 * s;
+        for (int b = 0; b < S->nstate; b++) {
+            if ((rc = make_map(&S->maps[b].qbox, L, S->state[b], 5, CXb, CYb)) || (rc = make_map(&S->maps[b].qint, L, S->state[b], 5, 32, ty)) ||
+                (rc = make_map(&S->maps[b].thbox, L, S->theta, 1, CXb, CYb)) || (rc = make_map(&S->maps[b].thint, L, S->theta, 1, 32, ty))) {
+                cudns_destroy(S); return rc;
+            }
+        }
+    }
     CK(cudaStreamSynchronize(S->st));
     *out = S;
     return CUDNS_OK;
@@ -317,7 +366,8 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
     p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
-    launch_rhs_stage(S->kc, p, c, S->st);
+    if (S->legacy_stage) launch_rhs_stage_smem(S->kc, p, c, S->st);
+    else launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
     S->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
@@ -490,7 +540,8 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
         CK(cudaEventRecord(e1, S->st));
         StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
         p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
-        launch_rhs_stage(S->kc, p, c, S->st);
+        if (S->legacy_stage) launch_rhs_stage_smem(S->kc, p, c, S->st);
+        else launch_rhs_stage(S->kc, p, c, S->maps[a], S->st);
         CK(cudaEventRecord(e2, S->st));
         int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc;
         CK(cudaEventRecord(e3, S->st));

@@ -1,5 +1,6 @@
 // Internal declarations of libcudns (not part of the C ABI).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
@@ -36,6 +37,9 @@ struct KConst {
     double aF[MAXS + 1];         // advective first-derivative weights a_l, l=1..s ( = -coeffF[s-l], globals.h:69-82)
     double aV[MAXS + 1];         // viscous   first-derivative weights
     double bV[MAXS + 1];         // viscous second-derivative weights b_0..b_v ( = coeffVS[v-l] )
+    // the same weights pre-scaled by the grid spacing of direction d (stage kernel): cC = -a_l/(4 dx_d) (split-form
+    // flux sums), cP = a_l/dx_d (pressure gradient, advective order), c1 = a_l/dx_d and c2 = b_l/dx_d^2 (viscous order)
+    double cC[3][MAXS + 1], cP[3][MAXS + 1], c1[3][MAXS + 1], c2[3][MAXS + 1];
     double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
@@ -69,8 +73,20 @@ struct StagePtrs {
     double *viscmax;             // optional: atomic max of mu-based dt limiter (stale-mu semantics)
 };
 
+// TMA descriptors of one state buffer (+ theta) for the stage kernel: the tile with its x/y stencil halos
+// ("box", (32+2*GX) x (TY+2s) x 1 plane x 5 fields) and the tile interior ("int", 32 x TY x 1 x 5)
+struct StageMaps {
+    CUtensorMap qbox, qint, thbox, thint;
+};
+#ifndef STAGE_TY
+#define STAGE_TY 12              // tile rows of the stage kernel (= warps per CTA)
+#endif
+int stage_tile_y();
+int stage_smem_bytes(int s, bool linear_visc);
+
 void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st);
-void launch_rhs_stage(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st);
+void launch_rhs_stage(const KConst &kc, const StagePtrs &p, const StageCoef &c, const StageMaps &maps, cudaStream_t st);
+void launch_rhs_stage_smem(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st);
 void launch_fill_xy(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_zwrap(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_pack_z(const KConst &kc, const double *q5, double *send_lo, double *send_hi, cudaStream_t st);

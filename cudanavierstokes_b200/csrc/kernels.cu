@@ -490,7 +490,7 @@ static void launch_rhs_stage_t(const KConst &kc, const StagePtrs &p, const Stage
     rhs_stage_kernel<S, V><<<grid, NTHREADS, smem, st>>>(kc, p, c, zchunk);
 }
 
-void launch_rhs_stage(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st) {
+void launch_rhs_stage_smem(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st) {
     switch (kc.s * 10 + kc.v) {
         case 11: launch_rhs_stage_t<1, 1>(kc, p, c, st); break;
         case 21: launch_rhs_stage_t<2, 1>(kc, p, c, st); break;
