@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcudns.so")
+LIB_PATH = os.environ.get("CUDNS_LIB", os.path.join(_HERE, "libcudns.so"))   # override: tuning builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 __all__ = ["Params", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",

@@ -44,7 +44,8 @@ template <int S, int TY, int NQ> struct Cfg {
     static constexpr int NEED = WPQ * COLS_THREAD;
     static constexpr int NCOLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;   // power of two >= 32
     static constexpr int NH = 2 * S * TY + 2 * S * TX;  // halo cells of one plane (no corners)
-    static constexpr size_t CUR_D = (size_t)2 * NQ * CSZ;
+    static constexpr int NP = (NQ + 1) / 2;             // quantity pairs of the shared plane (double2 cells)
+    static constexpr size_t CUR_D = (size_t)2 * 2 * NP * CSZ;
     static constexpr size_t BOX_D = (size_t)6 * CSZ;
     static constexpr size_t INT_D = (size_t)6 * NT;
     static constexpr size_t PRO_D = (size_t)2 * S * 6 * NT;
@@ -190,24 +191,26 @@ struct Sums {
     double lapu[3];       // sum_d D2_d u_m
     double dT[3], dth[3], dp[3], dmu[3];
     double lapT;
-    double rhs[5];        // convective part accumulates here directly
+    double rhs[5];        // the convective part accumulates here directly
 };
 
 // Accumulate everything direction D contributes.  fetch(l, P, M) delivers the NQ quantities at offsets +l / -l.
 // Coefficients are pre-scaled by the grid spacing: cC = -a_l/(4 dx), cP = a_l/dx, c1 = a_l/dx (viscous order), c2 = b_l/dx^2.
+// For the stretched wall-normal grid (D == 0, nonuni) the first-derivative sums and the convective sums still lack the
+// metric factor xp[i]; the caller applies it right after this call (x is processed first, so rhs holds x terms only).
 template <int D, int S, int V, int NQ, class Fetch>
-__device__ __forceinline__ void dir_sums(const KConst &c, const double (&C)[NQ], Fetch &&fetch, Sums &A, bool nonuni, double xpi, int i) {
+__device__ __forceinline__ void dir_sums(const KConst &c, const double (&C)[NQ], Fetch &&fetch, Sums &A, bool nonuni, int i) {
     const double Uc = C[ZU + D];
-    double aM = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, a4 = 0.0;
-    double d1u[3] = {0.0, 0.0, 0.0}, d2u[3], d1T = 0.0, d2T, d1th = 0.0, d1p = 0.0, d1mu = 0.0;
-    const double *tab = c.cVSx + i;        // non-uniform x only: cVSx[it*mx + i]
+    double aM = 0.0;
+    const double *tab = c.cVSx + i;        // non-uniform x only: cVSx[it*mx + i]  (cuda_utils.cu:107-122)
     const int mx = c.L.mx;
-    if (D == 0 && nonuni) {
-        const double cc = tab[(size_t)V * mx];
-        d2u[0] = cc * C[ZU]; d2u[1] = cc * C[ZV]; d2u[2] = cc * C[ZW]; d2T = cc * C[ZT];
-    } else {
-        d2u[0] = c.c2[D][0] * C[ZU]; d2u[1] = c.c2[D][0] * C[ZV]; d2u[2] = c.c2[D][0] * C[ZW]; d2T = c.c2[D][0] * C[ZT];
+    {
+        double k20 = c.c2[D][0];
+        if (D == 0 && nonuni) k20 = tab[(size_t)V * mx];
+        A.lapu[0] = fma(k20, C[ZU], A.lapu[0]); A.lapu[1] = fma(k20, C[ZV], A.lapu[1]); A.lapu[2] = fma(k20, C[ZW], A.lapu[2]);
+        A.lapT = fma(k20, C[ZT], A.lapT);
     }
+    A.g[0][D] = 0.0; A.g[1][D] = 0.0; A.g[2][D] = 0.0; A.dT[D] = 0.0; A.dth[D] = 0.0; A.dp[D] = 0.0; A.dmu[D] = 0.0;
 #pragma unroll
     for (int l = 1; l <= S; l++) {
         double Pn[NQ], Mn[NQ];
@@ -217,39 +220,32 @@ __device__ __forceinline__ void dir_sums(const KConst &c, const double (&C)[NQ],
         const double Ap = (C[ZR] + Pn[ZR]) * fma(c.cC[D][l], Pn[ZU + D], cu);
         const double Am = (C[ZR] + Mn[ZR]) * fma(c.cC[D][l], Mn[ZU + D], cu);
         aM += Ap - Am;
-        a0 = fma(Ap, Pn[ZU], a0); a0 = fma(-Am, Mn[ZU], a0);
-        a1 = fma(Ap, Pn[ZV], a1); a1 = fma(-Am, Mn[ZV], a1);
-        a2 = fma(Ap, Pn[ZW], a2); a2 = fma(-Am, Mn[ZW], a2);
-        a4 = fma(Ap, Pn[ZH], a4); a4 = fma(-Am, Mn[ZH], a4);
-        d1p = fma(c.cP[D][l], Pn[ZP] - Mn[ZP], d1p);
+        A.rhs[1] = fma(Ap, Pn[ZU], A.rhs[1]); A.rhs[1] = fma(-Am, Mn[ZU], A.rhs[1]);
+        A.rhs[2] = fma(Ap, Pn[ZV], A.rhs[2]); A.rhs[2] = fma(-Am, Mn[ZV], A.rhs[2]);
+        A.rhs[3] = fma(Ap, Pn[ZW], A.rhs[3]); A.rhs[3] = fma(-Am, Mn[ZW], A.rhs[3]);
+        A.rhs[4] = fma(Ap, Pn[ZH], A.rhs[4]); A.rhs[4] = fma(-Am, Mn[ZH], A.rhs[4]);
+        A.dp[D] = fma(c.cP[D][l], Pn[ZP] - Mn[ZP], A.dp[D]);
         if (l <= V) {
             double k2 = c.c2[D][l], k2m = k2;
             if (D == 0 && nonuni) { k2 = tab[(size_t)(V + l) * mx]; k2m = tab[(size_t)(V - l) * mx]; }
 #pragma unroll
             for (int m = 0; m < 3; m++) {
-                d1u[m] = fma(c.c1[D][l], Pn[ZU + m] - Mn[ZU + m], d1u[m]);
-                if (D == 0 && nonuni) { d2u[m] = fma(k2, Pn[ZU + m], d2u[m]); d2u[m] = fma(k2m, Mn[ZU + m], d2u[m]); }
-                else d2u[m] = fma(k2, Pn[ZU + m] + Mn[ZU + m], d2u[m]);
+                A.g[m][D] = fma(c.c1[D][l], Pn[ZU + m] - Mn[ZU + m], A.g[m][D]);
+                if (D == 0 && nonuni) { A.lapu[m] = fma(k2, Pn[ZU + m], A.lapu[m]); A.lapu[m] = fma(k2m, Mn[ZU + m], A.lapu[m]); }
+                else A.lapu[m] = fma(k2, Pn[ZU + m] + Mn[ZU + m], A.lapu[m]);
             }
-            d1T = fma(c.c1[D][l], Pn[ZT] - Mn[ZT], d1T);
-            if (D == 0 && nonuni) { d2T = fma(k2, Pn[ZT], d2T); d2T = fma(k2m, Mn[ZT], d2T); }
-            else d2T = fma(k2, Pn[ZT] + Mn[ZT], d2T);
-            d1th = fma(c.c1[D][l], Pn[ZD] - Mn[ZD], d1th);
-            if constexpr (NQ == 9) d1mu = fma(c.c1[D][l], Pn[ZM] - Mn[ZM], d1mu);
+            A.dT[D] = fma(c.c1[D][l], Pn[ZT] - Mn[ZT], A.dT[D]);
+            if (D == 0 && nonuni) { A.lapT = fma(k2, Pn[ZT], A.lapT); A.lapT = fma(k2m, Mn[ZT], A.lapT); }
+            else A.lapT = fma(k2, Pn[ZT] + Mn[ZT], A.lapT);
+            A.dth[D] = fma(c.c1[D][l], Pn[ZD] - Mn[ZD], A.dth[D]);
+            if constexpr (NQ == 9) A.dmu[D] = fma(c.c1[D][l], Pn[ZM] - Mn[ZM], A.dmu[D]);
         }
     }
-    if (D == 0 && nonuni) {      // metric of the stretched wall-normal grid (cuda_derivs.h:46-48,166-168,200-202)
-        d1u[0] *= xpi; d1u[1] *= xpi; d1u[2] *= xpi; d1T *= xpi; d1th *= xpi; d1p *= xpi; d1mu *= xpi;
-        aM *= xpi; a0 *= xpi; a1 *= xpi; a2 *= xpi; a4 *= xpi;
-    }
-    A.g[0][D] = d1u[0]; A.g[1][D] = d1u[1]; A.g[2][D] = d1u[2];
-    A.lapu[0] += d2u[0]; A.lapu[1] += d2u[1]; A.lapu[2] += d2u[2];
-    A.dT[D] = d1T; A.lapT += d2T; A.dth[D] = d1th; A.dp[D] = d1p; A.dmu[D] = d1mu;
-    A.rhs[0] += 2.0 * aM;
-    A.rhs[1] += fma(C[ZU], aM, a0);
-    A.rhs[2] += fma(C[ZV], aM, a1);
-    A.rhs[3] += fma(C[ZW], aM, a2);
-    A.rhs[4] += fma(C[ZH], aM, a4);
+    A.rhs[0] = fma(2.0, aM, A.rhs[0]);
+    A.rhs[1] = fma(C[ZU], aM, A.rhs[1]);
+    A.rhs[2] = fma(C[ZV], aM, A.rhs[2]);
+    A.rhs[3] = fma(C[ZW], aM, A.rhs[3]);
+    A.rhs[4] = fma(C[ZH], aM, A.rhs[4]);
 }
 
 template <int S, int V, int TY, int NQ>
@@ -257,9 +253,9 @@ __global__ void __launch_bounds__(TX *TY, 1)
 stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs P, const __grid_constant__ StageCoef sc, int zchunk,
              const __grid_constant__ StageMaps tm) {
     using G = Cfg<S, TY, NQ>;
-    constexpr int NT = G::NT, R = G::R, CY = G::CY, CSZ = G::CSZ;
+    constexpr int NT = G::NT, R = G::R, CSZ = G::CSZ, NP = G::NP;
     extern __shared__ __align__(1024) double smem[];
-    double *cur0 = smem;                               // [2][NQ][CY][CX]
+    double2 *cur0 = (double2 *)smem;                   // [2][NP][CY][CX] pairs (rho,u) (v,w) (H,p) (T,theta) (mu,-)
     double *boxraw = smem + G::CUR_D;                  // [6][CY][CX]   raw r,u,v,w,e,theta of the current plane with halos
     double *intraw = boxraw + G::BOX_D;                // [6][TY][TX]   raw fields of the plane S ahead (tile interior)
     uint64_t *mbar_p = (uint64_t *)(smem + G::DATA_D);
@@ -281,6 +277,14 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     const int nxt = min(TX, L.mx - i0);                // interior columns of this tile
     const bool nonuni = c.nonUniformX != 0;
     const bool bl = c.boundaryLayer != 0;
+    const size_t N = (size_t)L.mx * L.my * L.mz;
+    const size_t nxy = (size_t)L.mx * L.my;
+    const size_t gp0 = L.idx(ic, jc, 0), n0 = (size_t)ic + (size_t)jc * L.mx;
+    // periodic images this thread also writes (cross-shaped ghosts): perBCx / perBCy, boundary.h:38-46
+    const bool img_xlo = c.periodicX && i < S, img_xhi = c.periodicX && i >= L.mx - S;
+    const bool img_ylo = j < S, img_yhi = j >= L.my - S;
+    const bool do_update = active && !P.rhs_out;
+    const double dt = P.rhs_out ? 0.0 : *c.dt;
 
     const uint32_t mbar = smem_u32(mbar_p);
     if (ty == 0) tmem_alloc(smem_u32(tmem_holder), G::NCOLS);
@@ -328,6 +332,13 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         tma_load_4d(smem_u32(boxraw), &tm.qbox, mbar, i0, j0 + L.gy - S, k + L.gz, 0);
         tma_load_3d(smem_u32(boxraw + 5 * CSZ), &tm.thbox, mbar, i0, j0 + L.gy - S, k + L.gz);
     };
+    // quantity q of cell (cy,cx) in a pair-interleaved plane
+    auto cell = [&](double2 *pl, int q, int cy, int cx) -> double & { return ((double *)(pl + (q >> 1) * CSZ + cy * CX + cx))[q & 1]; };
+    auto store_cell = [&](double2 *pl, int cy, int cx, const double (&q)[NQ]) {
+        double2 *d = pl + cy * CX + cx;
+#pragma unroll
+        for (int n = 0; n < NP; n++) d[n * CSZ] = make_double2(q[2 * n], (2 * n + 1 < NQ) ? q[2 * n + 1] : 0.0);
+    };
 
     // ---- prologue: planes kbeg-S .. kbeg+S-1 into the ring (one batch of TMA loads into the whole buffer)
     uint32_t phase = 0;
@@ -347,7 +358,33 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     }
 
     for (int k = kbeg; k < kend; k++) {
-        double *cur = cur0 + (size_t)((k - kbeg) & 1) * NQ * CSZ;
+        double2 *cur = cur0 + (size_t)((k - kbeg) & 1) * NP * CSZ;
+        const size_t gp = gp0 + (size_t)(k + L.gz) * L.plane - (size_t)L.gz * L.plane + 0;   // = L.idx(ic,jc,k)
+        const size_t n = n0 + (size_t)k * nxy;
+        // ---- Runge-Kutta operands of this point: issued first so that their latency hides behind the whole plane
+        //      inc = Q_base (if it is not the input state) + dt (cA RA + cB RB);   rwo = wOld * RW
+        double inc[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, rwo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (do_update) {
+            if (P.RA) {
+#pragma unroll
+                for (int m = 0; m < 5; m++) inc[m] = sc.cA * P.RA[m * N + n];
+            }
+            if (P.RB) {
+#pragma unroll
+                for (int m = 0; m < 5; m++) inc[m] = fma(sc.cB, P.RB[m * N + n], inc[m]);
+            }
+#pragma unroll
+            for (int m = 0; m < 5; m++) inc[m] *= dt;
+            if (P.qbase != P.qin) {
+                const double rb = P.qbase[gp];
+                inc[0] += rb; inc[1] = fma(rb, P.qbase[vol + gp], inc[1]); inc[2] = fma(rb, P.qbase[2 * vol + gp], inc[2]);
+                inc[3] = fma(rb, P.qbase[3 * vol + gp], inc[3]); inc[4] += P.qbase[4 * vol + gp];
+            }
+            if (P.RW && sc.wOld != 0.0) {
+#pragma unroll
+                for (int m = 0; m < 5; m++) rwo[m] = sc.wOld * P.RW[m * N + n];
+            }
+        }
         mbar_wait(mbar, phase); phase ^= 1;
         ring_insert(k + S, intraw);
         if (bl && k == kglob_lo) ring_bottom_ghosts();
@@ -355,11 +392,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         double C[NQ];
         tmem_ld_slot<NQ>(tslot(k), C);
         const double e_c = boxraw[4 * CSZ + (ty + S) * CX + (tx + GX)];
-        {
-            double *d = cur + (ty + S) * CX + (tx + GX);
-#pragma unroll
-            for (int n = 0; n < NQ; n++) d[n * CSZ] = C[n];
-        }
+        store_cell(cur, ty + S, tx + GX, C);
         // ---- halo cells of plane k: raw -> EOS -> shared plane
         for (int cidx = tid; cidx < G::NH; cidx += NT) {
             int cx, cy;
@@ -370,9 +403,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             const double *s = boxraw + cy * CX + cx;
             double q[NQ];
             eos_q<NQ>(c, s[0], s[CSZ], s[2 * CSZ], s[3 * CSZ], s[4 * CSZ], s[5 * CSZ], q);
-            double *d = cur + cy * CX + cx;
-#pragma unroll
-            for (int n = 0; n < NQ; n++) d[n * CSZ] = q[n];
+            store_cell(cur, cy, cx, q);
         }
         __syncthreads();
         if (tid == 0 && k + 1 < kend) issue_plane_loads(k + 1);
@@ -383,67 +414,91 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
                 if (side == 0 && !xlo_tile) continue;
                 if (side == 1 && !xhi_tile) continue;
                 if (j0 + row >= L.my) continue;
-                double *rowp = cur + (row + S) * CX;
+                const int cy = row + S;
                 int cg, cm;             // ghost column, mirror column
                 double u, v, w, p, t, th;
                 if (side == 0) {
                     cg = GX - gq; cm = GX + gq - 1;   // cell mirror: f[-g] <- f[g-1]
-                    u = -rowp[ZU * CSZ + cm]; v = -rowp[ZV * CSZ + cm]; w = -rowp[ZW * CSZ + cm];     // wallBCxVel / botBCxExt(.,0)
-                    p = rowp[ZP * CSZ + cm];                                                         // wallBCxMir / botBCxMir
-                    th = rowp[ZD * CSZ + cm];                                                        // BCxNumber2
+                    u = -cell(cur, ZU, cy, cm); v = -cell(cur, ZV, cy, cm); w = -cell(cur, ZW, cy, cm);   // wallBCxVel / botBCxExt(.,0)
+                    p = cell(cur, ZP, cy, cm);                                                            // wallBCxMir / botBCxMir
+                    th = cell(cur, ZD, cy, cm);                                                           // BCxNumber2
                     if (bl) {
-                        t = rowp[ZT * CSZ + cm];                                                     // botBCxMir (adiabatic)
+                        t = cell(cur, ZT, cy, cm);                                                        // botBCxMir (adiabatic)
                         double pv;
-                        if (c.perturbed && perturb_u(c, j0 + row, k + c.kstart, pv)) u = pv;          // PerturbUvel
+                        if (c.perturbed && perturb_u(c, j0 + row, k + c.kstart, pv)) u = pv;               // PerturbUvel
                     } else {
-                        t = 2.0 * c.TwallBot - rowp[ZT * CSZ + cm];                                  // wallBCxExt
+                        t = 2.0 * c.TwallBot - cell(cur, ZT, cy, cm);                                     // wallBCxExt
                     }
                 } else {
                     int last = GX + nxt - 1;
                     cg = last + gq;
                     if (bl) {
                         cm = last - gq;         // node extrapolation topBCxExt: f[mx-1+g] = 2 f[mx-1] - f[mx-1-g]
-                        u = 2.0 * rowp[ZU * CSZ + last] - rowp[ZU * CSZ + cm];
-                        v = 2.0 * rowp[ZV * CSZ + last] - rowp[ZV * CSZ + cm];
-                        w = 2.0 * rowp[ZW * CSZ + last] - rowp[ZW * CSZ + cm];
-                        p = 2.0 * rowp[ZP * CSZ + last] - rowp[ZP * CSZ + cm];
-                        t = 2.0 * rowp[ZT * CSZ + last] - rowp[ZT * CSZ + cm];
-                        th = 2.0 * rowp[ZD * CSZ + last] - rowp[ZD * CSZ + cm];
+                        u = 2.0 * cell(cur, ZU, cy, last) - cell(cur, ZU, cy, cm);
+                        v = 2.0 * cell(cur, ZV, cy, last) - cell(cur, ZV, cy, cm);
+                        w = 2.0 * cell(cur, ZW, cy, last) - cell(cur, ZW, cy, cm);
+                        p = 2.0 * cell(cur, ZP, cy, last) - cell(cur, ZP, cy, cm);
+                        t = 2.0 * cell(cur, ZT, cy, last) - cell(cur, ZT, cy, cm);
+                        th = 2.0 * cell(cur, ZD, cy, last) - cell(cur, ZD, cy, cm);
                     } else {
                         cm = last - gq + 1;
-                        u = -rowp[ZU * CSZ + cm]; v = -rowp[ZV * CSZ + cm]; w = -rowp[ZW * CSZ + cm];
-                        p = rowp[ZP * CSZ + cm];
-                        th = rowp[ZD * CSZ + cm];
-                        t = 2.0 * c.TwallTop - rowp[ZT * CSZ + cm];
+                        u = -cell(cur, ZU, cy, cm); v = -cell(cur, ZV, cy, cm); w = -cell(cur, ZW, cy, cm);
+                        p = cell(cur, ZP, cy, cm);
+                        th = cell(cur, ZD, cy, cm);
+                        t = 2.0 * c.TwallTop - cell(cur, ZT, cy, cm);
                     }
                 }
-                rowp[ZU * CSZ + cg] = u; rowp[ZV * CSZ + cg] = v; rowp[ZW * CSZ + cg] = w;
-                rowp[ZP * CSZ + cg] = p; rowp[ZT * CSZ + cg] = t; rowp[ZD * CSZ + cg] = th;
-                if constexpr (NQ == 9) rowp[ZM * CSZ + cg] = visc_law(c, t);                              // mlBoundPT boundary.h:135
-                rowp[ZH * CSZ + cg] = t * c.Rgas * c.gam / (c.gam - 1.0) + 0.5 * (u * u + v * v + w * w);  // rhBoundPT boundary.h:121
-                rowp[ZR * CSZ + cg] = p / (c.Rgas * t);
+                double q[NQ];
+                q[ZU] = u; q[ZV] = v; q[ZW] = w; q[ZP] = p; q[ZT] = t; q[ZD] = th;
+                if constexpr (NQ == 9) q[NQ - 1] = visc_law(c, t);                                      // mlBoundPT boundary.h:135
+                q[ZH] = t * c.Rgas * c.gam / (c.gam - 1.0) + 0.5 * (u * u + v * v + w * w);             // rhBoundPT boundary.h:121
+                q[ZR] = p / (c.Rgas * t);
+                store_cell(cur, cy, cg, q);
             }
             __syncthreads();
         }
 
         // ---- the 48 directional stencil sums of point (i,j,k)
-        const double *curc = cur + (ty + S) * CX + (tx + GX);
-        const double xpi = nonuni ? c.xp[ic] : 1.0;
+        const double2 *curc = cur + (ty + S) * CX + (tx + GX);
         Sums A;
         A.lapu[0] = A.lapu[1] = A.lapu[2] = 0.0; A.lapT = 0.0;
 #pragma unroll
         for (int m = 0; m < 5; m++) A.rhs[m] = 0.0;
         dir_sums<0, S, V, NQ>(c, C, [&](int l, double (&Pn)[NQ], double (&Mn)[NQ]) {
 #pragma unroll
-            for (int n = 0; n < NQ; n++) { Pn[n] = curc[n * CSZ + l]; Mn[n] = curc[n * CSZ - l]; }
-        }, A, nonuni, xpi, ic);
+            for (int np = 0; np < NP; np++) {
+                if (np < 3 || l <= V) {
+                    const double2 a = curc[np * CSZ + l], b = curc[np * CSZ - l];
+                    Pn[2 * np] = a.x; Mn[2 * np] = b.x;
+                    if (2 * np + 1 < NQ) { Pn[2 * np + 1] = a.y; Mn[2 * np + 1] = b.y; }
+                } else {
+                    Pn[2 * np] = 0.0; Mn[2 * np] = 0.0;
+                    if (2 * np + 1 < NQ) { Pn[2 * np + 1] = 0.0; Mn[2 * np + 1] = 0.0; }
+                }
+            }
+        }, A, nonuni, ic);
+        if (nonuni) {      // metric of the stretched wall-normal grid (cuda_derivs.h:46-48,166-168,200-202)
+            const double xpi = c.xp[ic];
+            A.g[0][0] *= xpi; A.g[1][0] *= xpi; A.g[2][0] *= xpi; A.dT[0] *= xpi; A.dth[0] *= xpi; A.dp[0] *= xpi; A.dmu[0] *= xpi;
+#pragma unroll
+            for (int m = 0; m < 5; m++) A.rhs[m] *= xpi;
+        }
         dir_sums<1, S, V, NQ>(c, C, [&](int l, double (&Pn)[NQ], double (&Mn)[NQ]) {
 #pragma unroll
-            for (int n = 0; n < NQ; n++) { Pn[n] = curc[n * CSZ + l * CX]; Mn[n] = curc[n * CSZ - l * CX]; }
-        }, A, false, 1.0, ic);
+            for (int np = 0; np < NP; np++) {
+                if (np < 3 || l <= V) {
+                    const double2 a = curc[np * CSZ + l * CX], b = curc[np * CSZ - l * CX];
+                    Pn[2 * np] = a.x; Mn[2 * np] = b.x;
+                    if (2 * np + 1 < NQ) { Pn[2 * np + 1] = a.y; Mn[2 * np + 1] = b.y; }
+                } else {
+                    Pn[2 * np] = 0.0; Mn[2 * np] = 0.0;
+                    if (2 * np + 1 < NQ) { Pn[2 * np + 1] = 0.0; Mn[2 * np + 1] = 0.0; }
+                }
+            }
+        }, A, false, ic);
         dir_sums<2, S, V, NQ>(c, C, [&](int l, double (&Pn)[NQ], double (&Mn)[NQ]) {
             tmem_ld_pair<NQ>(tslot(k + l), tslot(k - l), Pn, Mn);
-        }, A, false, 1.0, ic);
+        }, A, false, ic);
 
         // ---- stress, dissipation, heat flux, pressure gradient: assembled once per point (cuda_rhs.cu:52-127,169-259,303-393)
         const double mu = (NQ == 9) ? C[NQ - 1] : C[ZT] * c.invRe;
@@ -492,44 +547,32 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             rhs[4] += sg * (c.sref[4 * nq + qi] - e_c);
         }
         if (active) {
-            const size_t gp = L.idx(i, j, k);
-            const size_t N = (size_t)L.mx * L.my * L.mz;
-            const size_t n = (size_t)i + (size_t)j * L.mx + (size_t)k * L.mx * L.my;
             if (P.rhs_out) {
 #pragma unroll
                 for (int m = 0; m < 5; m++) P.rhs_out[m * N + n] = rhs[m];
             } else {
                 // Runge-Kutta register update (sumLowStorageRK3 cuda_main.cu:244, eulerSum*/rk3final* :188-216)
-                const double dt = *c.dt;
-                double qb[5];
-                if (P.qbase == P.qin) { qb[0] = C[ZR]; qb[1] = C[ZR] * C[ZU]; qb[2] = C[ZR] * C[ZV]; qb[3] = C[ZR] * C[ZW]; qb[4] = e_c; }
-                else {
-                    double rb = P.qbase[gp];
-                    qb[0] = rb; qb[1] = rb * P.qbase[vol + gp]; qb[2] = rb * P.qbase[2 * vol + gp]; qb[3] = rb * P.qbase[3 * vol + gp];
-                    qb[4] = P.qbase[4 * vol + gp];
+                if (P.qbase == P.qin) {
+                    inc[0] += C[ZR]; inc[1] = fma(C[ZR], C[ZU], inc[1]); inc[2] = fma(C[ZR], C[ZV], inc[2]);
+                    inc[3] = fma(C[ZR], C[ZW], inc[3]); inc[4] += e_c;
                 }
+                const double dtn = dt * sc.cN;
                 double qn[5];
 #pragma unroll
                 for (int m = 0; m < 5; m++) {
-                    double inc = sc.cN * rhs[m];
-                    if (P.RA) inc += sc.cA * P.RA[m * N + n];
-                    if (P.RB) inc += sc.cB * P.RB[m * N + n];
-                    qn[m] = qb[m] + dt * inc;
-                    if (P.RW) P.RW[m * N + n] = (sc.wOld != 0.0) ? sc.wOld * P.RW[m * N + n] + sc.wNew * rhs[m] : sc.wNew * rhs[m];
+                    qn[m] = fma(dtn, rhs[m], inc[m]);
+                    if (P.RW) P.RW[m * N + n] = fma(sc.wNew, rhs[m], rwo[m]);
                 }
                 const double rn = 1.0 / qn[0];                                                   // deviceDiv cuda_math.cu:36
                 double out[5] = {qn[0], qn[1] * rn, qn[2] * rn, qn[3] * rn, qn[4]};
 #pragma unroll
                 for (int m = 0; m < 5; m++) {
-                    double *f = P.qout + m * vol;
-                    f[gp] = out[m];
-                    // periodic images (cross-shaped ghosts): perBCx / perBCy, boundary.h:38-46
-                    if (c.periodicX) {
-                        if (i < S) f[gp + L.mx] = out[m];
-                        if (i >= L.mx - S) f[gp - L.mx] = out[m];
-                    }
-                    if (j < S) f[gp + (size_t)L.my * L.px] = out[m];
-                    if (j >= L.my - S) f[gp - (size_t)L.my * L.px] = out[m];
+                    double *f = P.qout + m * vol + gp;
+                    f[0] = out[m];
+                    if (img_xlo) f[L.mx] = out[m];
+                    if (img_xhi) f[-(ptrdiff_t)L.mx] = out[m];
+                    if (img_ylo) f[(size_t)L.my * L.px] = out[m];
+                    if (img_yhi) f[-(ptrdiff_t)((size_t)L.my * L.px)] = out[m];
                 }
             }
         }
