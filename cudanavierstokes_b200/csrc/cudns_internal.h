@@ -79,7 +79,7 @@ struct StageMaps {
     CUtensorMap qbox, qint, thbox, thint;
 };
 #ifndef STAGE_TY
-#define STAGE_TY 12              // tile rows of the stage kernel (= warps per CTA)
+#define STAGE_TY 8              // tile rows of the stage kernel (= warps per CTA)
 #endif
 int stage_tile_y();
 int stage_smem_bytes(int s, bool linear_visc);

@@ -94,57 +94,69 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-#define R16(a, o) "=r"(a[o + 0]), "=r"(a[o + 1]), "=r"(a[o + 2]), "=r"(a[o + 3]), "=r"(a[o + 4]), "=r"(a[o + 5]), "=r"(a[o + 6]), "=r"(a[o + 7]), \
-                  "=r"(a[o + 8]), "=r"(a[o + 9]), "=r"(a[o + 10]), "=r"(a[o + 11]), "=r"(a[o + 12]), "=r"(a[o + 13]), "=r"(a[o + 14]), "=r"(a[o + 15])
-#define I16(a, o) "r"(a[o + 0]), "r"(a[o + 1]), "r"(a[o + 2]), "r"(a[o + 3]), "r"(a[o + 4]), "r"(a[o + 5]), "r"(a[o + 6]), "r"(a[o + 7]), \
-                  "r"(a[o + 8]), "r"(a[o + 9]), "r"(a[o + 10]), "r"(a[o + 11]), "r"(a[o + 12]), "r"(a[o + 13]), "r"(a[o + 14]), "r"(a[o + 15])
-
-// The load and its wait share one asm statement so that the compiler cannot schedule a use of the outputs before the wait.
+// The loads, their wait and the 2x32-bit -> double packing share one asm statement: the compiler cannot schedule a use
+// before the wait, and ptxas allocates the 32-bit destinations as the halves of the 64-bit results (no moves).
 template <int NQ> __device__ __forceinline__ void tmem_ld_slot(uint32_t ta, double (&q)[NQ]) {
-    uint32_t a[2 * NQ];
     if constexpr (NQ == 8) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-                     "tcgen05.wait::ld.sync.aligned;"
-                     : R16(a, 0) : "r"(ta) : "memory");
+        asm volatile("{\n\t.reg .b32 a<16>;\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {a0,a1,a2,a3,a4,a5,a6,a7,a8,a9,a10,a11,a12,a13,a14,a15}, [%8];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;\n\t"
+                     "mov.b64 %0, {a0,a1};\n\tmov.b64 %1, {a2,a3};\n\tmov.b64 %2, {a4,a5};\n\tmov.b64 %3, {a6,a7};\n\t"
+                     "mov.b64 %4, {a8,a9};\n\tmov.b64 %5, {a10,a11};\n\tmov.b64 %6, {a12,a13};\n\tmov.b64 %7, {a14,a15};\n\t}"
+                     : "=d"(q[0]), "=d"(q[1]), "=d"(q[2]), "=d"(q[3]), "=d"(q[4]), "=d"(q[5]), "=d"(q[6]), "=d"(q[7])
+                     : "r"(ta) : "memory");
     } else {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%18];\n\t"
-                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%16,%17}, [%19];\n\t"
-                     "tcgen05.wait::ld.sync.aligned;"
-                     : R16(a, 0), "=r"(a[16]), "=r"(a[17]) : "r"(ta), "r"(ta + 16) : "memory");
+        asm volatile("{\n\t.reg .b32 a<18>;\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {a0,a1,a2,a3,a4,a5,a6,a7,a8,a9,a10,a11,a12,a13,a14,a15}, [%9];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {a16,a17}, [%10];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;\n\t"
+                     "mov.b64 %0, {a0,a1};\n\tmov.b64 %1, {a2,a3};\n\tmov.b64 %2, {a4,a5};\n\tmov.b64 %3, {a6,a7};\n\t"
+                     "mov.b64 %4, {a8,a9};\n\tmov.b64 %5, {a10,a11};\n\tmov.b64 %6, {a12,a13};\n\tmov.b64 %7, {a14,a15};\n\t"
+                     "mov.b64 %8, {a16,a17};\n\t}"
+                     : "=d"(q[0]), "=d"(q[1]), "=d"(q[2]), "=d"(q[3]), "=d"(q[4]), "=d"(q[5]), "=d"(q[6]), "=d"(q[7]), "=d"(q[NQ - 1])
+                     : "r"(ta), "r"(ta + 16) : "memory");
     }
-#pragma unroll
-    for (int n = 0; n < NQ; n++) q[n] = __hiloint2double((int)a[2 * n + 1], (int)a[2 * n]);
 }
 template <int NQ> __device__ __forceinline__ void tmem_ld_pair(uint32_t ta, uint32_t tb, double (&p)[NQ], double (&m)[NQ]) {
-    uint32_t a[2 * NQ], b[2 * NQ];
     if constexpr (NQ == 8) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%32];\n\t"
-                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%33];\n\t"
-                     "tcgen05.wait::ld.sync.aligned;"
-                     : R16(a, 0), R16(b, 0) : "r"(ta), "r"(tb) : "memory");
+        asm volatile("{\n\t.reg .b32 a<16>;\n\t.reg .b32 b<16>;\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {a0,a1,a2,a3,a4,a5,a6,a7,a8,a9,a10,a11,a12,a13,a14,a15}, [%16];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {b0,b1,b2,b3,b4,b5,b6,b7,b8,b9,b10,b11,b12,b13,b14,b15}, [%17];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;\n\t"
+                     "mov.b64 %0, {a0,a1};\n\tmov.b64 %1, {a2,a3};\n\tmov.b64 %2, {a4,a5};\n\tmov.b64 %3, {a6,a7};\n\t"
+                     "mov.b64 %4, {a8,a9};\n\tmov.b64 %5, {a10,a11};\n\tmov.b64 %6, {a12,a13};\n\tmov.b64 %7, {a14,a15};\n\t"
+                     "mov.b64 %8, {b0,b1};\n\tmov.b64 %9, {b2,b3};\n\tmov.b64 %10, {b4,b5};\n\tmov.b64 %11, {b6,b7};\n\t"
+                     "mov.b64 %12, {b8,b9};\n\tmov.b64 %13, {b10,b11};\n\tmov.b64 %14, {b12,b13};\n\tmov.b64 %15, {b14,b15};\n\t}"
+                     : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3]), "=d"(p[4]), "=d"(p[5]), "=d"(p[6]), "=d"(p[7]),
+                       "=d"(m[0]), "=d"(m[1]), "=d"(m[2]), "=d"(m[3]), "=d"(m[4]), "=d"(m[5]), "=d"(m[6]), "=d"(m[7])
+                     : "r"(ta), "r"(tb) : "memory");
     } else {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%36];\n\t"
-                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%37];\n\t"
-                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%32,%33}, [%38];\n\t"
-                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%34,%35}, [%39];\n\t"
-                     "tcgen05.wait::ld.sync.aligned;"
-                     : R16(a, 0), R16(b, 0), "=r"(a[16]), "=r"(a[17]), "=r"(b[16]), "=r"(b[17])
+        asm volatile("{\n\t.reg .b32 a<18>;\n\t.reg .b32 b<18>;\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {a0,a1,a2,a3,a4,a5,a6,a7,a8,a9,a10,a11,a12,a13,a14,a15}, [%18];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {b0,b1,b2,b3,b4,b5,b6,b7,b8,b9,b10,b11,b12,b13,b14,b15}, [%19];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {a16,a17}, [%20];\n\t"
+                     "tcgen05.ld.sync.aligned.32x32b.x2.b32 {b16,b17}, [%21];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;\n\t"
+                     "mov.b64 %0, {a0,a1};\n\tmov.b64 %1, {a2,a3};\n\tmov.b64 %2, {a4,a5};\n\tmov.b64 %3, {a6,a7};\n\t"
+                     "mov.b64 %4, {a8,a9};\n\tmov.b64 %5, {a10,a11};\n\tmov.b64 %6, {a12,a13};\n\tmov.b64 %7, {a14,a15};\n\t"
+                     "mov.b64 %8, {a16,a17};\n\t"
+                     "mov.b64 %9, {b0,b1};\n\tmov.b64 %10, {b2,b3};\n\tmov.b64 %11, {b4,b5};\n\tmov.b64 %12, {b6,b7};\n\t"
+                     "mov.b64 %13, {b8,b9};\n\tmov.b64 %14, {b10,b11};\n\tmov.b64 %15, {b12,b13};\n\tmov.b64 %16, {b14,b15};\n\t"
+                     "mov.b64 %17, {b16,b17};\n\t}"
+                     : "=d"(p[0]), "=d"(p[1]), "=d"(p[2]), "=d"(p[3]), "=d"(p[4]), "=d"(p[5]), "=d"(p[6]), "=d"(p[7]), "=d"(p[NQ - 1]),
+                       "=d"(m[0]), "=d"(m[1]), "=d"(m[2]), "=d"(m[3]), "=d"(m[4]), "=d"(m[5]), "=d"(m[6]), "=d"(m[7]), "=d"(m[NQ - 1])
                      : "r"(ta), "r"(tb), "r"(ta + 16), "r"(tb + 16) : "memory");
-    }
-#pragma unroll
-    for (int n = 0; n < NQ; n++) {
-        p[n] = __hiloint2double((int)a[2 * n + 1], (int)a[2 * n]);
-        m[n] = __hiloint2double((int)b[2 * n + 1], (int)b[2 * n]);
     }
 }
 template <int NQ> __device__ __forceinline__ void tmem_st_slot(uint32_t ta, const double (&q)[NQ]) {
-    uint32_t a[2 * NQ];
-#pragma unroll
-    for (int n = 0; n < NQ; n++) { a[2 * n] = (uint32_t)__double2loint(q[n]); a[2 * n + 1] = (uint32_t)__double2hiint(q[n]); }
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(ta), I16(a, 0) : "memory");
+    asm volatile("{\n\t.reg .b32 a<16>;\n\t"
+                 "mov.b64 {a0,a1}, %1;\n\tmov.b64 {a2,a3}, %2;\n\tmov.b64 {a4,a5}, %3;\n\tmov.b64 {a6,a7}, %4;\n\t"
+                 "mov.b64 {a8,a9}, %5;\n\tmov.b64 {a10,a11}, %6;\n\tmov.b64 {a12,a13}, %7;\n\tmov.b64 {a14,a15}, %8;\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {a0,a1,a2,a3,a4,a5,a6,a7,a8,a9,a10,a11,a12,a13,a14,a15};\n\t}"
+                 ::"r"(ta), "d"(q[0]), "d"(q[1]), "d"(q[2]), "d"(q[3]), "d"(q[4]), "d"(q[5]), "d"(q[6]), "d"(q[7]) : "memory");
     if constexpr (NQ == 9)
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(ta + 16), "r"(a[16]), "r"(a[17]) : "memory");
+        asm volatile("{\n\t.reg .b32 a<2>;\n\tmov.b64 {a0,a1}, %1;\n\ttcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {a0,a1};\n\t}"
+                     ::"r"(ta + 16), "d"(q[NQ - 1]) : "memory");
     tmem_wait_st();
 }
 
@@ -283,6 +295,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     // periodic images this thread also writes (cross-shaped ghosts): perBCx / perBCy, boundary.h:38-46
     const bool img_xlo = c.periodicX && i < S, img_xhi = c.periodicX && i >= L.mx - S;
     const bool img_ylo = j < S, img_yhi = j >= L.my - S;
+    const bool img_any = img_xlo || img_xhi || img_ylo || img_yhi;
     const bool do_update = active && !P.rhs_out;
     const double dt = P.rhs_out ? 0.0 : *c.dt;
 
@@ -295,9 +308,11 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     const uint32_t tmem0 = *tmem_holder;
     const uint32_t tbase = tmem0 + ((uint32_t)(32 * (ty & 3)) << 16) + (uint32_t)((ty >> 2) * G::COLS_THREAD);
     auto tslot = [&](int kk) -> uint32_t { return tbase + (uint32_t)(((kk + 16 * R) % R) * G::COLS_SLOT); };
+    // the same for kk = k + l with |l| <= S, given s0 = k mod R (no division in the plane loop)
+    auto tslot_rel = [&](int s0, int l) -> uint32_t { int t = s0 + l; t = t >= R ? t - R : t; t = t < 0 ? t + R : t; return tbase + (uint32_t)(t * G::COLS_SLOT); };
 
     // raw fields of plane kk at this thread's column (src = [6][NT]) -> EOS -> ring slot
-    auto ring_insert = [&](int kk, const double *src) {
+    auto ring_insert = [&](int kk, const double *src, uint32_t slot) {
         double q[NQ];
         if (bl && (kk < kglob_lo || kk >= kglob_hi)) {
             if (kk >= kglob_hi) {
@@ -307,12 +322,12 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
                 tmem_ld_pair<NQ>(tslot(kglob_hi - 1), tslot(kglob_hi - 1 - gq), a, b);
 #pragma unroll
                 for (int n = 0; n < NQ; n++) q[n] = 2.0 * a[n] - b[n];
-                tmem_st_slot<NQ>(tslot(kk), q);
+                tmem_st_slot<NQ>(slot, q);
             }
             return;      // bottom ghosts are generated once plane kglob_lo+S is in (ring_bottom_ghosts)
         }
         eos_q<NQ>(c, src[tid], src[NT + tid], src[2 * NT + tid], src[3 * NT + tid], src[4 * NT + tid], src[5 * NT + tid], q);
-        tmem_st_slot<NQ>(tslot(kk), q);
+        tmem_st_slot<NQ>(slot, q);
     };
     // botBCzExt (boundary.h:158-160): f[-g] = 2 f[0] - f[g]
     auto ring_bottom_ghosts = [&]() {
@@ -352,45 +367,45 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             }
         }
         mbar_wait(mbar, phase); phase ^= 1;
-        for (int n = 0; n < 2 * S; n++) ring_insert(kbeg - S + n, pro + (size_t)n * 6 * NT);
+        for (int n = 0; n < 2 * S; n++) ring_insert(kbeg - S + n, pro + (size_t)n * 6 * NT, tslot(kbeg - S + n));
         __syncthreads();
         if (tid == 0) issue_plane_loads(kbeg);
     }
 
-    for (int k = kbeg; k < kend; k++) {
+    int s0 = (kbeg + 16 * R) % R;
+    for (int k = kbeg; k < kend; k++, s0 = (s0 + 1 == R) ? 0 : s0 + 1) {
         double2 *cur = cur0 + (size_t)((k - kbeg) & 1) * NP * CSZ;
-        const size_t gp = gp0 + (size_t)(k + L.gz) * L.plane - (size_t)L.gz * L.plane + 0;   // = L.idx(ic,jc,k)
+        const size_t gp = gp0 + (size_t)k * L.plane;          // = L.idx(ic,jc,k)
         const size_t n = n0 + (size_t)k * nxy;
-        // ---- Runge-Kutta operands of this point: issued first so that their latency hides behind the whole plane
-        //      inc = Q_base (if it is not the input state) + dt (cA RA + cB RB);   rwo = wOld * RW
-        double inc[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, rwo[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        // ---- Runge-Kutta operands of this point: the loads are issued first so that their latency hides behind the whole
+        //      plane; they are only consumed in the update at the bottom of the loop body
+        double ra[5], rb[5], qv[5], rw[5];
+#pragma unroll
+        for (int m = 0; m < 5; m++) { ra[m] = 0.0; rb[m] = 0.0; qv[m] = 0.0; rw[m] = 0.0; }
         if (do_update) {
             if (P.RA) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) inc[m] = sc.cA * P.RA[m * N + n];
+                for (int m = 0; m < 5; m++) ra[m] = P.RA[m * N + n];
             }
             if (P.RB) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) inc[m] = fma(sc.cB, P.RB[m * N + n], inc[m]);
+                for (int m = 0; m < 5; m++) rb[m] = P.RB[m * N + n];
             }
-#pragma unroll
-            for (int m = 0; m < 5; m++) inc[m] *= dt;
             if (P.qbase != P.qin) {
-                const double rb = P.qbase[gp];
-                inc[0] += rb; inc[1] = fma(rb, P.qbase[vol + gp], inc[1]); inc[2] = fma(rb, P.qbase[2 * vol + gp], inc[2]);
-                inc[3] = fma(rb, P.qbase[3 * vol + gp], inc[3]); inc[4] += P.qbase[4 * vol + gp];
+#pragma unroll
+                for (int m = 0; m < 5; m++) qv[m] = P.qbase[m * vol + gp];
             }
             if (P.RW && sc.wOld != 0.0) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) rwo[m] = sc.wOld * P.RW[m * N + n];
+                for (int m = 0; m < 5; m++) rw[m] = P.RW[m * N + n];
             }
         }
         mbar_wait(mbar, phase); phase ^= 1;
-        ring_insert(k + S, intraw);
+        ring_insert(k + S, intraw, tslot_rel(s0, S));
         if (bl && k == kglob_lo) ring_bottom_ghosts();
         // ---- own point of plane k: out of the ring into registers and into the shared plane
         double C[NQ];
-        tmem_ld_slot<NQ>(tslot(k), C);
+        tmem_ld_slot<NQ>(tslot_rel(s0, 0), C);
         const double e_c = boxraw[4 * CSZ + (ty + S) * CX + (tx + GX)];
         store_cell(cur, ty + S, tx + GX, C);
         // ---- halo cells of plane k: raw -> EOS -> shared plane
@@ -497,7 +512,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             }
         }, A, false, ic);
         dir_sums<2, S, V, NQ>(c, C, [&](int l, double (&Pn)[NQ], double (&Mn)[NQ]) {
-            tmem_ld_pair<NQ>(tslot(k + l), tslot(k - l), Pn, Mn);
+            tmem_ld_pair<NQ>(tslot_rel(s0, l), tslot_rel(s0, -l), Pn, Mn);
         }, A, false, ic);
 
         // ---- stress, dissipation, heat flux, pressure gradient: assembled once per point (cuda_rhs.cu:52-127,169-259,303-393)
@@ -551,28 +566,32 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
 #pragma unroll
                 for (int m = 0; m < 5; m++) P.rhs_out[m * N + n] = rhs[m];
             } else {
-                // Runge-Kutta register update (sumLowStorageRK3 cuda_main.cu:244, eulerSum*/rk3final* :188-216)
-                if (P.qbase == P.qin) {
-                    inc[0] += C[ZR]; inc[1] = fma(C[ZR], C[ZU], inc[1]); inc[2] = fma(C[ZR], C[ZV], inc[2]);
-                    inc[3] = fma(C[ZR], C[ZW], inc[3]); inc[4] += e_c;
-                }
-                const double dtn = dt * sc.cN;
+                // Runge-Kutta register update (sumLowStorageRK3 cuda_main.cu:244, eulerSum*/rk3final* :188-216):
+                //   Q_out = Q_base + dt (cN K + cA RA + cB RB),   RW = wOld RW + wNew K
+                double qb[5];
+                if (P.qbase == P.qin) { qb[0] = C[ZR]; qb[1] = C[ZR] * C[ZU]; qb[2] = C[ZR] * C[ZV]; qb[3] = C[ZR] * C[ZW]; qb[4] = e_c; }
+                else { qb[0] = qv[0]; qb[1] = qv[0] * qv[1]; qb[2] = qv[0] * qv[2]; qb[3] = qv[0] * qv[3]; qb[4] = qv[4]; }
                 double qn[5];
 #pragma unroll
                 for (int m = 0; m < 5; m++) {
-                    qn[m] = fma(dtn, rhs[m], inc[m]);
-                    if (P.RW) P.RW[m * N + n] = fma(sc.wNew, rhs[m], rwo[m]);
+                    const double k_all = fma(sc.cN, rhs[m], fma(sc.cA, ra[m], sc.cB * rb[m]));
+                    qn[m] = fma(dt, k_all, qb[m]);
+                    if (P.RW) P.RW[m * N + n] = fma(sc.wNew, rhs[m], sc.wOld * rw[m]);
                 }
                 const double rn = 1.0 / qn[0];                                                   // deviceDiv cuda_math.cu:36
-                double out[5] = {qn[0], qn[1] * rn, qn[2] * rn, qn[3] * rn, qn[4]};
+                const double out[5] = {qn[0], qn[1] * rn, qn[2] * rn, qn[3] * rn, qn[4]};
+                double *f = P.qout + gp;
 #pragma unroll
-                for (int m = 0; m < 5; m++) {
-                    double *f = P.qout + m * vol + gp;
-                    f[0] = out[m];
-                    if (img_xlo) f[L.mx] = out[m];
-                    if (img_xhi) f[-(ptrdiff_t)L.mx] = out[m];
-                    if (img_ylo) f[(size_t)L.my * L.px] = out[m];
-                    if (img_yhi) f[-(ptrdiff_t)((size_t)L.my * L.px)] = out[m];
+                for (int m = 0; m < 5; m++) f[m * vol] = out[m];
+                if (img_any) {
+#pragma unroll
+                    for (int m = 0; m < 5; m++) {
+                        double *fm = f + m * vol;
+                        if (img_xlo) fm[L.mx] = out[m];
+                        if (img_xhi) fm[-(ptrdiff_t)L.mx] = out[m];
+                        if (img_ylo) fm[(size_t)L.my * L.px] = out[m];
+                        if (img_yhi) fm[-(ptrdiff_t)((size_t)L.my * L.px)] = out[m];
+                    }
                 }
             }
         }
