@@ -10,6 +10,8 @@
 // (cuda_derivs.h:30-155 evaluates the same sum as a difference of two interface fluxes).
 #include "cudns_internal.h"
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 
 namespace cudns {
 
@@ -122,7 +124,10 @@ __global__ void __launch_bounds__(256) theta_kernel(KConst c, const double *__re
     }
 }
 
+void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaStream_t st);   // theta.cu
 void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st) {
+    static const bool legacy = [] { const char *e = getenv("CUDNS_THETA"); return e && std::string(e) == "legacy"; }();
+    if (!legacy) { launch_theta_march(kc, q, theta, st); return; }
     dim3 grid((kc.L.mx + 31) / 32, (kc.L.my + 7) / 8, (kc.L.mz + 2 * kc.v + 7) / 8);
     switch (kc.v) {
         case 1: theta_kernel<1><<<grid, 256, 0, st>>>(kc, q, theta); break;
