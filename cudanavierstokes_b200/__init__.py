@@ -62,11 +62,11 @@ class Params(C.Structure):
 
 def build(force=False, verbose=False):
     """compile libcudns.so in-tree for sm_100a (nvcc cross-compiles without a GPU)"""
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp", ".h", "Makefile"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp", ".h", ".inc", "Makefile"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "cudns.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
-        out = subprocess.run(["make", "-C", CSRC] + (["-B"] if force else []), capture_output=True, text=True)
+        out = subprocess.run(["make", "-j8", "-C", CSRC] + (["-B"] if force else []), capture_output=True, text=True)
         if verbose or out.returncode:
             print(out.stdout[-4000:], out.stderr[-4000:])
         if out.returncode:

@@ -46,8 +46,10 @@ struct cudns_solver {
     cudns_exchange_fn exchange; void *exchange_user;
     uint64_t launches, stages;
     size_t bytes;
-    StageMaps maps[3];           // TMA descriptors of state[b] (+ theta)
-    bool legacy_stage;           // CUDNS_STAGE=smem: first-generation shared-memory-ring kernel (A/B timing only)
+    StageMaps maps[3];           // TMA descriptors of state[b] (+ theta), tile of the second-generation kernel
+    StageMaps lmaps[3];          // the same for the tile of the lean kernel
+    CUtensorMap rmap[2];         // R1 / R2 (unpadded register arrays), tile interior of the lean kernel
+    int stage_gen;               // 3: lean kernel (default); CUDNS_STAGE=tmem -> 2, CUDNS_STAGE=smem -> 1 (A/B timing only)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcudns does not link libcuda)
@@ -75,6 +77,20 @@ static int make_map(CUtensorMap *m, const Layout &L, double *base, int nf, int b
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return CUDNS_ECUDA; }
+    return CUDNS_OK;
+}
+
+// unpadded register array [5][mz][my][mx] -> descriptor with box 32 x ty x 1 x 5
+static int make_rmap(CUtensorMap *m, const Layout &L, double *base, int ty) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CUDNS_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)L.mx, (cuuint64_t)L.my, (cuuint64_t)L.mz, 5};
+    cuuint64_t strides[3] = {(cuuint64_t)L.mx * 8, (cuuint64_t)L.mx * L.my * 8, (cuuint64_t)L.mx * L.my * L.mz * 8};
+    cuuint32_t box[4] = {32, (cuuint32_t)ty, 1, 5};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (register array) failed with CUresult " + std::to_string((int)r)); return CUDNS_ECUDA; }
     return CUDNS_OK;
 }
 
@@ -145,6 +161,11 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     for (int d = 0; d < 3; d++) {
         for (int l = 1; l <= s; l++) { kc.cC[d][l] = -0.25 * kc.aF[l] * kc.d1[d]; kc.cP[d][l] = kc.aF[l] * kc.d1[d]; }
         for (int l = 0; l <= v; l++) { kc.c1[d][l] = kc.aV[l] * kc.d1[d]; kc.c2[d][l] = kc.bV[l] * kc.d2[d]; }
+        for (int l = 0; l <= MAXS; l++) {
+            kc.cf[d][l][0] = kc.cC[d][l]; kc.cf[d][l][1] = -kc.cP[d][l]; kc.cf[d][l][2] = kc.c1[d][l]; kc.cf[d][l][3] = kc.c2[d][l];
+            kc.c1t[d][l] = kc.c1[d][l] / 3.0;
+        }
+        kc.c20sum += kc.c2[d][0];
     }
     kc.gam = p->gam;
     kc.Rgas = (1.f / (p->gam * p->Ma * p->Ma));                 // globals.h:48
@@ -185,10 +206,11 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
     {
         const char *env = getenv("CUDNS_STAGE");
-        S->legacy_stage = env && std::string(env) == "smem";
+        S->stage_gen = !env ? 3 : std::string(env) == "smem" ? 1 : std::string(env) == "tmem" ? 2 : 3;
     }
     if ((size_t)stage_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin ||
-        (size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+        (size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin ||
+        (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
         const int ty = stage_tile_y(), CXb = 32 + 2 * GX, CYb = ty + 2 * s;
         for (int b = 0; b < S->nstate; b++) {
@@ -197,6 +219,14 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
                 cudns_destroy(S); return rc;
             }
         }
+        const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lty + 2 * s;
+        for (int b = 0; b < S->nstate; b++) {
+            if ((rc = make_map(&S->lmaps[b].qbox, L, S->state[b], 5, CXb, LYb)) || (rc = make_map(&S->lmaps[b].qint, L, S->state[b], 5, 32, lty)) ||
+                (rc = make_map(&S->lmaps[b].thbox, L, S->theta, 1, CXb, LYb)) || (rc = make_map(&S->lmaps[b].thint, L, S->theta, 1, 32, lty))) {
+                cudns_destroy(S); return rc;
+            }
+        }
+        if ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty)))) { cudns_destroy(S); return rc; }
     }
     CK(cudaStreamSynchronize(S->st));
     *out = S;
@@ -359,6 +389,22 @@ int cudns_get_scalars(cudns_handle S, double *dt, double *dpdz, double *time) {
 
 }  // extern "C"
 
+// the stage kernel of the selected generation; p.qin = state[in], p.qbase = state[base]
+static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoef &c, int in, int base) {
+    const bool lean_ok = !(p.RB && p.RW && c.wOld != 0.0);      // the lean kernel stages at most one of RB / old RW
+    if (S->stage_gen == 1) launch_rhs_stage_smem(S->kc, p, c, S->st);
+    else if (S->stage_gen == 2 || !lean_ok) launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
+    else {
+        LeanMaps m;
+        m.qbox = S->lmaps[in].qbox; m.qint = S->lmaps[in].qint; m.thbox = S->lmaps[in].thbox; m.thint = S->lmaps[in].thint;
+        m.qbint = S->lmaps[base].qint;
+        auto rmap_of = [&](const double *r) -> const CUtensorMap & { return (r == S->R2) ? S->rmap[1] : S->rmap[0]; };
+        m.opa = rmap_of(p.RA);
+        m.opb = rmap_of(p.RB ? p.RB : p.RW);
+        launch_rhs_stage_lean(S->kc, p, c, m, S->st);
+    }
+}
+
 // one RHS evaluation + register update: K = RHS(state[in]); see StageCoef
 static int run_stage(cudns_solver *S, int in, int base, int out, const double *RA, const double *RB, double *RW,
                      const StageCoef &c, double *rhs_out) {
@@ -366,8 +412,7 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
     p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
-    if (S->legacy_stage) launch_rhs_stage_smem(S->kc, p, c, S->st);
-    else launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
+    launch_stage_any(S, p, c, in, base);
     S->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
@@ -540,8 +585,7 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
         CK(cudaEventRecord(e1, S->st));
         StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
         p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
-        if (S->legacy_stage) launch_rhs_stage_smem(S->kc, p, c, S->st);
-        else launch_rhs_stage(S->kc, p, c, S->maps[a], S->st);
+        launch_stage_any(S, p, c, a, a);
         CK(cudaEventRecord(e2, S->st));
         int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc;
         CK(cudaEventRecord(e3, S->st));

@@ -40,6 +40,9 @@ struct KConst {
     // the same weights pre-scaled by the grid spacing of direction d (stage kernel): cC = -a_l/(4 dx_d) (split-form
     // flux sums), cP = a_l/dx_d (pressure gradient, advective order), c1 = a_l/dx_d and c2 = b_l/dx_d^2 (viscous order)
     double cC[3][MAXS + 1], cP[3][MAXS + 1], c1[3][MAXS + 1], c2[3][MAXS + 1];
+    // lean stage kernel: cf[d][l] = { -a_l/(4 dx_d), -a_l/dx_d (advective order), a_l/dx_d, b_l/dx_d^2 (viscous order) },
+    // c1t = a_l/(3 dx_d) (viscous order), c20sum = sum_d b_0/dx_d^2
+    double cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
     double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
@@ -81,6 +84,19 @@ struct StageMaps {
 #ifndef STAGE_TY
 #define STAGE_TY 8              // tile rows of the stage kernel (= warps per CTA)
 #endif
+// ---- lean stage kernel (stage_lean.inc): tile rows per CTA for the linear-viscosity (8 quantities) and the general
+// (9 quantities) variants, and its TMA descriptors
+#ifndef CUDNS_LEAN_TY_LINEAR
+#define CUDNS_LEAN_TY_LINEAR 12
+#endif
+#define CUDNS_LEAN_TY_GENERAL 8
+struct LeanMaps {
+    CUtensorMap qbox, qint, thbox, thint;   // input state / theta: halo'd tile and tile interior
+    CUtensorMap qbint;                      // base state, tile interior (Kutta RK3 / RK4)
+    CUtensorMap opa, opb;                   // RA ; RB or the old RW (unpadded register arrays, tile interior)
+};
+void launch_rhs_stage_lean(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, cudaStream_t st);
+int lean_smem_bytes(int s, bool linear_visc);
 int stage_tile_y();
 int stage_smem_bytes(int s, bool linear_visc);
 

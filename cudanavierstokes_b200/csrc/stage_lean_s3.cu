@@ -1,0 +1,18 @@
+// stage kernel instantiations for stencilSize = 3 (see stage_lean.inc)
+#define LEAN_TY8 CUDNS_LEAN_TY_LINEAR
+#define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
+#include "stage_lean.inc"
+namespace cudns {
+void launch_lean_s3(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, cudaStream_t st) {
+    using namespace lean;
+    switch (kc.v) {
+        case 1: launch_v<3, 1>(kc, p, c, maps, gen, st); break;
+        case 2: launch_v<3, 2>(kc, p, c, maps, gen, st); break;
+        case 3: launch_v<3, 3>(kc, p, c, maps, gen, st); break;
+        default: break;
+    }
+}
+int lean_smem_s3(bool linear_visc) {
+    return (int)(linear_visc ? lean::Cfg<3, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<3, CUDNS_LEAN_TY_GENERAL, 9>::bytes);
+}
+}  // namespace cudns
