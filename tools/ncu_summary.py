@@ -19,11 +19,13 @@ for k in keys:
         if h == k or h.startswith(k):
             print("%-75s %s %s" % (h, M[h], units[hdr.index(h)])); break
 wp = npts / 32
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 try:
-    print("instr / point: %.1f   fp64 instr / point: %.1f" % (float(M["smsp__inst_executed.sum"].replace(",", "")) / wp,
-          float(M.get("smsp__inst_executed_pipe_fp64.sum", "0").replace(",", "")) / wp))
-    rd = float(M["dram__bytes_read.sum"].replace(",", "")); wr = float(M["dram__bytes_write.sum"].replace(",", ""))
-    print("dram bytes / point: read %.1f write %.1f (units: %s)" % (rd / npts, wr / npts, units[hdr.index("dram__bytes_read.sum")]))
+    print("warp instr / warp-point: %.1f" % (float(M["smsp__inst_executed.sum"].replace(",", "")) / wp))
+    rd = float(M["dram__bytes_read.sum"].replace(",", "")) * SCALE[units[hdr.index("dram__bytes_read.sum")]]
+    wr = float(M["dram__bytes_write.sum"].replace(",", "")) * SCALE[units[hdr.index("dram__bytes_write.sum")]]
+    print("dram bytes / launch: read %.4g write %.4g total %.4g   per point: read %.1f write %.1f total %.1f" %
+          (rd, wr, rd + wr, rd / npts, wr / npts, (rd + wr) / npts))
 except Exception as e:
     print("derived metrics unavailable:", e)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
