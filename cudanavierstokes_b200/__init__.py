@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CUDNS_LIB", os.path.join(_HERE, "libcudns.so"))   # override: tuning builds only
 CSRC = os.path.join(_HERE, "csrc")
 
-__all__ = ["Params", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",
+__all__ = ["Params", "PeerInfo", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",
            "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "EXPORTS"]
 
 # every symbol include/cudns.h declares (checked by tests/test_abi.py)
@@ -58,6 +58,12 @@ class Params(C.Structure):
         ("nranks", C.c_int), ("rank", C.c_int), ("device", C.c_int),
         ("reserved", C.c_int * 5),
     ]
+
+
+class PeerInfo(C.Structure):
+    """struct cudns_peer_info (include/cudns.h): what a rank publishes so that its z-slab neighbours can map its state block"""
+    _fields_ = [("mem_handle", C.c_ubyte * 64), ("device", C.c_int), ("pid", C.c_int),
+                ("local_ptr", C.c_uint64), ("block_bytes", C.c_uint64)]
 
 
 def build(force=False, verbose=False):
@@ -116,6 +122,8 @@ def lib():
     L.cudns_calc_bulk.argtypes = [H, dp, dp]
     L.cudns_get_scalars.argtypes = [H, dp, dp, dp]
     L.cudns_set_dt.argtypes = [H, C.c_double, C.c_int]
+    L.cudns_halo_local_info.argtypes = [H, C.POINTER(PeerInfo)]
+    L.cudns_halo_connect.argtypes = [H, C.POINTER(PeerInfo), C.POINTER(PeerInfo)]
     L.cudns_halo_buffers.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.cudns_set_allreduce.argtypes = [H, ALLREDUCE_FN, C.c_void_p]
@@ -316,6 +324,17 @@ class Solver:
         p = [C.c_void_p() for _ in range(4)]; n = C.c_size_t(0)
         _check(self.L.cudns_halo_buffers(self.h, *[C.byref(q) for q in p], C.byref(n)))
         return [q.value for q in p], n.value
+
+    def halo_local_info(self):
+        """bytes of this rank's cudns_peer_info (CUDA IPC handle of the state block), to be sent to the slab neighbours"""
+        pi = PeerInfo(); _check(self.L.cudns_halo_local_info(self.h, C.byref(pi)))
+        return bytes(pi)
+
+    def halo_connect(self, lower, upper):
+        """map the neighbours' state blocks (bytes from their halo_local_info): from now on the stage kernel writes their
+        ghost planes directly over NVLink and no pack / exchange / unpack kernels run inside the step loop"""
+        lo = PeerInfo.from_buffer_copy(lower); up = PeerInfo.from_buffer_copy(upper)
+        _check(self.L.cudns_halo_connect(self.h, C.byref(lo), C.byref(up)))
 
     def set_allreduce(self, fn):
         """fn(device_ptr:int, n:int, op:int) with op 0 min, 1 sum, 2 max; must act on the solver's stream"""

@@ -33,8 +33,15 @@ struct cudns_solver {
     Layout L;
     size_t N;                    // local interior points
     cudaStream_t st;
-    double *state[3];            // padded 5-field buffers
+    double *block;               // ONE allocation: nstate padded 5-field buffers + the neighbour mailbox (a single IPC handle covers it)
+    size_t block_doubles;        // state part of the block, in doubles; the mailbox (8 x u64) follows
+    double *state[3];            // padded 5-field buffers inside block
     int nstate, cur;
+    // peer-memory halo transport (cudns_halo_connect): the neighbours' blocks mapped into this process
+    double *peer_lo, *peer_hi;   // nullptr: not connected / no such neighbour
+    void *ipc_lo, *ipc_hi;       // what cudaIpcOpenMemHandle returned (to close), nullptr for same-process peers
+    bool connected;
+    unsigned long long epoch;    // stage counter of the hand-shake
     double *theta;
     double *R1, *R2;
     double *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
@@ -127,10 +134,11 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     S->N = (size_t)mx * my * mzl;
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     S->nstate = (p->lowStorage && !p->rk4) ? 2 : 3;
-    for (int b = 0; b < S->nstate; b++) {
-        if ((rc = dmalloc(S, &S->state[b], 5 * L.vol))) { cudns_destroy(S); return rc; }
-        CK(cudaMemsetAsync(S->state[b], 0, 5 * L.vol * sizeof(double), S->st));
-    }
+    S->block_doubles = (size_t)S->nstate * 5 * L.vol;
+    S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
+    if ((rc = dmalloc(S, &S->block, S->block_doubles + 32))) { cudns_destroy(S); return rc; }
+    CK(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(double), S->st));
+    for (int b = 0; b < S->nstate; b++) S->state[b] = S->block + (size_t)b * 5 * L.vol;
     if ((rc = dmalloc(S, &S->theta, L.vol))) { cudns_destroy(S); return rc; }
     CK(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
     if ((rc = dmalloc(S, &S->R1, 5 * S->N))) { cudns_destroy(S); return rc; }
@@ -237,7 +245,9 @@ int cudns_destroy(cudns_handle S) {
     if (!S) return CUDNS_OK;
     cudaSetDevice(S->P.device);
     if (S->st) cudaStreamSynchronize(S->st);
-    for (int b = 0; b < 3; b++) cudaFree(S->state[b]);
+    if (S->ipc_lo) cudaIpcCloseMemHandle(S->ipc_lo);
+    if (S->ipc_hi && S->ipc_hi != S->ipc_lo) cudaIpcCloseMemHandle(S->ipc_hi);
+    cudaFree(S->block);
     cudaFree(S->theta); cudaFree(S->R1); cudaFree(S->R2);
     cudaFree(S->d_xp); cudaFree(S->d_cVSx); cudaFree(S->d_dxv); cudaFree(S->d_spx); cudaFree(S->d_spz); cudaFree(S->d_sref);
     cudaFree(S->d_scal); cudaFree(S->d_hist);
@@ -268,14 +278,55 @@ int cudns_halo_buffers(cudns_handle S, void **send_lo, void **send_hi, void **re
     return CUDNS_OK;
 }
 int cudns_halo_local_info(cudns_handle S, cudns_peer_info *mine) {
-    if (!S || !mine) return CUDNS_EINVAL;
-    set_error("peer-memory halo transport is not built yet (round 2); use cudns_set_exchange");
-    return CUDNS_EUNSUPPORTED;
+    if (!S || !mine) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    std::memset(mine, 0, sizeof(*mine));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, S->block));
+    static_assert(sizeof(h) == CUDNS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    std::memcpy(mine->mem_handle, &h, sizeof(h));
+    mine->device = S->P.device;
+    mine->pid = (int)getpid();
+    mine->local_ptr = (uint64_t)(uintptr_t)S->block;
+    mine->block_bytes = (uint64_t)(S->block_doubles + 32) * sizeof(double);
+    return CUDNS_OK;
 }
-int cudns_halo_connect(cudns_handle S, const cudns_peer_info *, const cudns_peer_info *) {
-    if (!S) return CUDNS_EINVAL;
-    set_error("peer-memory halo transport is not built yet (round 2); use cudns_set_exchange");
-    return CUDNS_EUNSUPPORTED;
+
+// map one neighbour's block: same process -> its pointer (peer access enabled), other process -> CUDA IPC
+static int open_peer(cudns_solver *S, const cudns_peer_info *pi, double **ptr, void **ipc) {
+    *ptr = nullptr; *ipc = nullptr;
+    if (pi->block_bytes != (uint64_t)(S->block_doubles + 32) * sizeof(double)) { set_error("neighbour block size differs (unequal slabs?)"); return CUDNS_EINVAL; }
+    if (pi->pid == (int)getpid()) {
+        if (pi->device != S->P.device) {
+            int can = 0; CK(cudaDeviceCanAccessPeer(&can, S->P.device, pi->device));
+            if (!can) { set_error("no peer access between the neighbour devices"); return CUDNS_EUNSUPPORTED; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(pi->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
+            cudaGetLastError();
+        }
+        *ptr = (double *)(uintptr_t)pi->local_ptr;
+        return CUDNS_OK;
+    }
+    cudaIpcMemHandle_t h; std::memcpy(&h, pi->mem_handle, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
+    *ptr = (double *)p; *ipc = p;
+    return CUDNS_OK;
+}
+
+int cudns_halo_connect(cudns_handle S, const cudns_peer_info *lower, const cudns_peer_info *upper) {
+    if (!S || !lower || !upper) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (S->P.nranks < 2) { set_error("cudns_halo_connect needs nranks > 1"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    int rc;
+    if ((rc = open_peer(S, lower, &S->peer_lo, &S->ipc_lo))) return rc;
+    const bool same = lower->pid == upper->pid && lower->device == upper->device && lower->local_ptr == upper->local_ptr &&
+                      std::memcmp(lower->mem_handle, upper->mem_handle, CUDNS_IPC_HANDLE_BYTES) == 0;
+    if (same) { S->peer_hi = S->peer_lo; S->ipc_hi = S->ipc_lo; }
+    else if ((rc = open_peer(S, upper, &S->peer_hi, &S->ipc_hi))) return rc;
+    S->connected = true;
+    return CUDNS_OK;
 }
 int cudns_get_counters(cudns_handle S, uint64_t *kernel_launches, uint64_t *rk_stages) {
     if (!S) return CUDNS_EINVAL;
@@ -391,7 +442,7 @@ int cudns_get_scalars(cudns_handle S, double *dt, double *dpdz, double *time) {
 
 // the stage kernel of the selected generation; p.qin = state[in], p.qbase = state[base]
 static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoef &c, int in, int base) {
-    const bool lean_ok = !(p.RB && p.RW && c.wOld != 0.0);      // the lean kernel stages at most one of RB / old RW
+    const bool lean_ok = true;      // (no scheme of cudns_advance needs RB and the old RW in the same stage)
     if (S->stage_gen == 1) launch_rhs_stage_smem(S->kc, p, c, S->st);
     else if (S->stage_gen == 2 || !lean_ok) launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
     else {
@@ -405,6 +456,36 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
     }
 }
 
+// does this solver's stage kernel write the z ghost planes itself (lean kernel; on one device always, across devices once
+// the peer blocks are mapped)?
+static bool inkernel_ghosts(const cudns_solver *S) { return S->stage_gen == 3 && (S->P.nranks == 1 || S->connected); }
+
+// neighbour-side addresses of output buffer `out` for the stage kernel (see StagePtrs::qout_lo / qout_hi)
+static void ghost_targets(cudns_solver *S, int out, StagePtrs &p) {
+    p.qout_lo = nullptr; p.qout_hi = nullptr;
+    if (!inkernel_ghosts(S)) return;
+    const size_t off = (size_t)out * 5 * S->L.vol;
+    const bool bl = S->P.boundaryLayer != 0;                  // z is not periodic: the global bottom / top have no neighbour
+    if (S->P.nranks == 1) { if (!bl) { p.qout_lo = S->state[out]; p.qout_hi = S->state[out]; } return; }
+    if (!(bl && S->P.rank == 0)) p.qout_lo = S->peer_lo + off;
+    if (!(bl && S->P.rank == S->P.nranks - 1)) p.qout_hi = S->peer_hi + off;
+}
+
+// after a stage kernel that wrote the neighbours' ghost planes: tell them, and wait for theirs
+static void handshake(cudns_solver *S) {
+    if (S->P.nranks == 1) return;
+    const bool bl = S->P.boundaryLayer != 0;
+    const bool has_lo = !(bl && S->P.rank == 0), has_hi = !(bl && S->P.rank == S->P.nranks - 1);
+    S->epoch++;
+    unsigned long long *mine = (unsigned long long *)(S->block + S->block_doubles);
+    // my planes go into the lower neighbour's UPPER ghosts: its slot 1 ("written by the upper one"), and vice versa
+    unsigned long long *lo_slot = has_lo ? (unsigned long long *)(S->peer_lo + S->block_doubles) + 1 : nullptr;
+    unsigned long long *hi_slot = has_hi ? (unsigned long long *)(S->peer_hi + S->block_doubles) + 0 : nullptr;
+    launch_halo_signal(lo_slot, hi_slot, S->epoch, S->st);
+    launch_halo_wait(mine, has_lo, has_hi, S->epoch, S->st);
+    S->launches += 2;
+}
+
 // one RHS evaluation + register update: K = RHS(state[in]); see StageCoef
 static int run_stage(cudns_solver *S, int in, int base, int out, const double *RA, const double *RB, double *RW,
                      const StageCoef &c, double *rhs_out) {
@@ -412,11 +493,17 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
     p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
+    ghost_targets(S, out, p);
+    if (rhs_out) { p.qout_lo = nullptr; p.qout_hi = nullptr; }
     launch_stage_any(S, p, c, in, base);
     S->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
-    if (!rhs_out) { int rc = fill_z_ghosts(S, S->state[out]); if (rc) return rc; S->stages++; }
+    if (!rhs_out) {
+        if (inkernel_ghosts(S)) handshake(S);
+        else { int rc = fill_z_ghosts(S, S->state[out]); if (rc) return rc; }
+        S->stages++;
+    }
     return CUDNS_OK;
 }
 
@@ -585,9 +672,11 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
         CK(cudaEventRecord(e1, S->st));
         StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
         p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
+        ghost_targets(S, b, p);
         launch_stage_any(S, p, c, a, a);
         CK(cudaEventRecord(e2, S->st));
-        int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc;
+        if (inkernel_ghosts(S)) handshake(S);
+        else { int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc; }
         CK(cudaEventRecord(e3, S->st));
         CK(cudaEventSynchronize(e3));
         float x; cudaEventElapsedTime(&x, e0, e1); t_th += x; cudaEventElapsedTime(&x, e1, e2); t_rhs += x; cudaEventElapsedTime(&x, e2, e3); t_h += x;

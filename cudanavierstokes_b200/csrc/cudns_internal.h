@@ -72,6 +72,9 @@ struct StagePtrs {
     const double *theta;         // padded
     const double *RA, *RB;       // 5 unpadded fields each (stride N) or nullptr
     double *RW;                  // 5 unpadded fields or nullptr
+    double *qout_lo, *qout_hi;   // lean kernel: the SAME output buffer on the lower / upper z neighbour (peer memory over NVLink,
+                                 // or qout itself for the periodic wrap on one device); the stage kernel stores its first / last
+                                 // gz planes straight into the neighbour's ghost planes.  nullptr: no such neighbour / not connected
     double *rhs_out;             // test path: write K only (5 unpadded) and skip the update
     double *viscmax;             // optional: atomic max of mu-based dt limiter (stale-mu semantics)
 };
@@ -113,6 +116,9 @@ void launch_unpad(const KConst &kc, const double *q5, double *dst5[5], cudaStrea
 void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st);
 void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st);
 void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
+// cross-GPU stage hand-shake over peer memory: store `epoch` into the two neighbours' mailbox slots / spin until both own slots reach it
+void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st);
+void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, cudaStream_t st);
 
 int rhs_stage_smem_bytes(int s);
 bool rhs_stage_supported(int s, int v);

@@ -731,4 +731,34 @@ void launch_dt_combine(double *dt, const double *conv, const double *visc, doubl
     scalar_kernel<<<1, 1, 0, st>>>(0, dt, conv, visc, cfl);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// stage hand-shake between z-slab neighbours (replaces the host-side MPI_Sendrecv + cudaDeviceSynchronize of
+// updateHaloFive, comm.cpp:114-134).  The stage kernel has already stored its boundary planes into the neighbours'
+// ghost planes; the signal makes them visible (system-scope release) and tells the neighbour which stage they belong to.
+// ---------------------------------------------------------------------------------------------
+__global__ void halo_signal_kernel(unsigned long long *lo_slot, unsigned long long *hi_slot, unsigned long long epoch) {
+    __threadfence_system();
+    if (lo_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(lo_slot), "l"(epoch) : "memory");
+    if (hi_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hi_slot), "l"(epoch) : "memory");
+}
+__global__ void halo_wait_kernel(const unsigned long long *slots, int need_lo, int need_hi, unsigned long long epoch) {
+    // slots[0]: written by the lower neighbour, slots[1]: by the upper one
+    for (int n = 0; n < 2; n++) {
+        if (!(n == 0 ? need_lo : need_hi)) continue;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slots + n) : "memory");
+            if (v < epoch) __nanosleep(200);
+        } while (v < epoch);
+    }
+    __threadfence_system();
+}
+void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st) {
+    halo_signal_kernel<<<1, 1, 0, st>>>(peer_lo_slot, peer_hi_slot, epoch);
+}
+void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, cudaStream_t st) {
+    halo_wait_kernel<<<1, 1, 0, st>>>(my_slots, need_lo, need_hi, epoch);
+}
+
 }  // namespace cudns

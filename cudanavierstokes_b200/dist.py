@@ -57,8 +57,15 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": (ndoubles,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def attach(solver, dist=None):
-    """wire a Solver (nranks > 1) to torch.distributed: NCCL send/recv for the halo blocks, all_reduce for dt/bulk.
+def attach(solver, dist=None, peer=True):
+    """wire a Solver (nranks > 1) to torch.distributed.
+
+    * scalar reductions (dt: MIN/MAX, bulk/forcing: SUM): NCCL all_reduce on the solver's stream;
+    * halo transport inside the step loop: peer memory (``peer=True``, default) -- the ranks swap the CUDA IPC handles of
+      their state blocks once (all_gather_object), after which the stage kernel stores its boundary planes straight into
+      the neighbours' ghost planes over NVLink and a device-side flag replaces the exchange; if the handles cannot be
+      mapped (or ``peer=False``) the stage falls back to pack -> NCCL send/recv -> unpack on the solver's stream;
+    * the one-off ghost fill of cudns_set_state always uses the send/recv path.
 
     Everything is enqueued on the solver's stream (torch.cuda.ExternalStream), nothing synchronises the host.
     """
@@ -91,6 +98,21 @@ def attach(solver, dist=None):
     solver.set_exchange(exchange)
     solver.set_allreduce(allreduce)
     solver._dist_keep = (bufs, ext)
+    solver.peer_transport = False
+    if peer:
+        infos = [None] * nranks
+        td.all_gather_object(infos, solver.halo_local_info())
+        lo, up = neighbours(rank, nranks)
+        ok = 1
+        try:
+            solver.halo_connect(infos[lo], infos[up])
+        except Exception as e:                      # e.g. no peer access between the two devices
+            ok = 0; solver._peer_error = str(e)
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        td.all_reduce(flag, op=td.ReduceOp.MIN)     # all ranks or none: the hand-shake needs both sides
+        if int(flag.item()) != 1:
+            raise RuntimeError("peer-memory halo transport unavailable on some rank: %s" % getattr(solver, "_peer_error", "(other rank)"))
+        solver.peer_transport = True
     return solver
 
 

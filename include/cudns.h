@@ -139,18 +139,21 @@ int cudns_set_dt(cudns_handle h, double dt, int fixed);
  *      fillBoundaries[Five] cuda_utils.cu:597-778) ------------------------------------------
  * z-slab neighbours exchange (s+v) full padded planes of the 5 state fields once per RK stage.
  * Two transports:
- *  (a) peer memory: each rank publishes a CUDA IPC handle of its state allocation; after
- *      cudns_halo_connect() the stage kernels' epilogue copies boundary planes straight into the
- *      neighbour's ghost planes over NVLink and signals with device-side flags;
+ *  (a) peer memory: each rank publishes a CUDA IPC handle of its state allocation
+ *      (cudns_halo_local_info); after cudns_halo_connect() the stage kernel stores its first / last
+ *      (s+v) planes straight into the neighbours' ghost planes over NVLink while it computes, and a
+ *      device-side epoch flag per neighbour replaces the host synchronisation;
  *  (b) external: the caller moves the bytes (e.g. NCCL send/recv on views of the buffers returned
  *      by cudns_halo_buffers) between cudns_stage_begin/cudns_stage_end.
  * Scalar reductions (dt: MIN, bulk/forcing: SUM) are delegated to a caller-provided callback so the
  * library does not link an MPI or NCCL of its own. */
 #define CUDNS_IPC_HANDLE_BYTES 64
 typedef struct cudns_peer_info {
-    unsigned char mem_handle[CUDNS_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the halo mailbox */
+    unsigned char mem_handle[CUDNS_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the solver's state block (+ mailbox) */
     int device;
     int pid;
+    uint64_t local_ptr;          /* the block's address in the owning process (used when both ranks share a process) */
+    uint64_t block_bytes;        /* size of the block: must be equal on neighbouring ranks */
 } cudns_peer_info;
 int cudns_halo_local_info(cudns_handle h, cudns_peer_info *mine);
 /* lower = rank-1 (periodic), upper = rank+1 (periodic) */
