@@ -11,7 +11,8 @@ stencilVisc = 4), default 512^3 (BASELINE config 5 / north_star target; every fi
     python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--scheme ls3|kutta3|rk4] [--impl reference]
 
 N > 1: launched by torch.distributed.run, one rank per GPU, z-slab decomposition of the SAME global grid (strong
-scaling), halo planes exchanged with NCCL on the solver's stream.
+scaling); the stage kernel stores its boundary planes straight into the neighbours' ghost planes over NVLink peer memory
+(CUDA IPC handles swapped once through torch.distributed), scalar reductions go through NCCL on the solver's stream.
 
 --impl reference: the reference has no CPU implementation; the arm times the CPU oracle
 (oracle/, an OpenMP restatement of the reference's algorithm, kind "port") on this box's host cores.
@@ -245,7 +246,7 @@ def main():
     peak, peak_kind = measured_peak()
     alg = ALG_BYTES[scheme] * npts / world                           # bytes per launch of the stage kernel on one rank
     ach = alg / (prof["rhs_stage_ms"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "rhs_stage_kernel", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
+    roofline = {"bound": "hbm", "kernel": "lean::stage_kernel (fused RHS + RK stage update + halo stores)", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
                 "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("rhs_stage_%d" % n),
                 "alg_bytes_per_launch": alg, "kernel_ms": prof["rhs_stage_ms"], "theta_ms": prof["theta_ms"],
                 "zghost_ms": prof["halo_ms"],
@@ -284,6 +285,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "tgv%d_s4v4_fp64_%s" % (n, scheme), "grid": [n, n, n], "scheme": scheme,
                            "stages_per_step": stages, "stencilSize": 4, "stencilVisc": 4, "decomposition": "z-slabs x%d" % world,
+                           "halo": ("peer-memory stores from the stage kernel over NVLink (CUDA IPC) + device-side epoch flags"
+                                    if world > 1 else "periodic z wrap stored by the stage kernel"),
                            "cache": "inputs larger than L2 (each of the >=16 resident fields is %.2f GiB)" % (npts * 8 / 2 ** 30)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "hbm_gbs_whole_step": ALG_BYTES[scheme] * value * 1e6 / 1e9}
