@@ -56,6 +56,9 @@ struct cudns_solver {
     StageMaps maps[3];           // TMA descriptors of state[b] (+ theta), tile of the second-generation kernel
     StageMaps lmaps[3];          // the same for the tile of the lean kernel
     CUtensorMap rmap[2];         // R1 / R2 (unpadded register arrays), tile interior of the lean kernel
+    StageMaps wmaps[3];          // tile of the wide (16-warp) lean kernel
+    CUtensorMap wrmap[2];
+    bool wide;                   // the wide variant applies to this configuration (CUDNS_WIDE=0 disables it)
     int stage_gen;               // 3: lean kernel (default); CUDNS_STAGE=tmem -> 2, CUDNS_STAGE=smem -> 1 (A/B timing only)
 };
 
@@ -173,6 +176,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             kc.cf[d][l][0] = kc.cC[d][l]; kc.cf[d][l][1] = -kc.cP[d][l]; kc.cf[d][l][2] = kc.c1[d][l]; kc.cf[d][l][3] = kc.c2[d][l];
             kc.c1t[d][l] = kc.c1[d][l] / 3.0;
         }
+        if (d == 2) for (int l = 0; l <= MAXS; l++) kc.cfzp[l] = -kc.cP[2][l] * (1.f / (p->gam * p->Ma * p->Ma));
         kc.c20sum += kc.c2[d][0];
     }
     kc.gam = p->gam;
@@ -235,6 +239,18 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             }
         }
         if ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty)))) { cudns_destroy(S); return rc; }
+        const char *we = getenv("CUDNS_WIDE");
+        S->wide = lean_wide_ok(kc) && !(we && std::string(we) == "0") && (size_t)lean_smem_wide_bytes(s) <= prop.sharedMemPerBlockOptin;
+        if (S->wide) {
+            const int wty = CUDNS_LEAN_TY_WIDE, WYb = wty + 2 * s;
+            for (int b = 0; b < S->nstate; b++) {
+                if ((rc = make_map(&S->wmaps[b].qbox, L, S->state[b], 5, CXb, WYb)) || (rc = make_map(&S->wmaps[b].qint, L, S->state[b], 5, 32, wty)) ||
+                    (rc = make_map(&S->wmaps[b].thbox, L, S->theta, 1, CXb, WYb)) || (rc = make_map(&S->wmaps[b].thint, L, S->theta, 1, 32, wty))) {
+                    cudns_destroy(S); return rc;
+                }
+            }
+            if ((rc = make_rmap(&S->wrmap[0], L, S->R1, wty)) || (S->R2 && (rc = make_rmap(&S->wrmap[1], L, S->R2, wty)))) { cudns_destroy(S); return rc; }
+        }
     }
     CK(cudaStreamSynchronize(S->st));
     *out = S;
@@ -446,13 +462,17 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
     if (S->stage_gen == 1) launch_rhs_stage_smem(S->kc, p, c, S->st);
     else if (S->stage_gen == 2 || !lean_ok) launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
     else {
+        // the wide variant stages one operand tile only (RA): every low-storage RK3 stage and the test path qualify
+        const bool wide = S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
+        const StageMaps *sm = wide ? S->wmaps : S->lmaps;
+        const CUtensorMap *rm = wide ? S->wrmap : S->rmap;
         LeanMaps m;
-        m.qbox = S->lmaps[in].qbox; m.qint = S->lmaps[in].qint; m.thbox = S->lmaps[in].thbox; m.thint = S->lmaps[in].thint;
-        m.qbint = S->lmaps[base].qint;
-        auto rmap_of = [&](const double *r) -> const CUtensorMap & { return (r == S->R2) ? S->rmap[1] : S->rmap[0]; };
+        m.qbox = sm[in].qbox; m.qint = sm[in].qint; m.thbox = sm[in].thbox; m.thint = sm[in].thint;
+        m.qbint = sm[base].qint;
+        auto rmap_of = [&](const double *r) -> const CUtensorMap & { return (r == S->R2) ? rm[1] : rm[0]; };
         m.opa = rmap_of(p.RA);
         m.opb = rmap_of(p.RB ? p.RB : p.RW);
-        launch_rhs_stage_lean(S->kc, p, c, m, S->st);
+        launch_rhs_stage_lean(S->kc, p, c, m, wide, S->st);
     }
 }
 

@@ -43,6 +43,7 @@ struct KConst {
     // lean stage kernel: cf[d][l] = { -a_l/(4 dx_d), -a_l/dx_d (advective order), a_l/dx_d, b_l/dx_d^2 (viscous order) },
     // c1t = a_l/(3 dx_d) (viscous order), c20sum = sum_d b_0/dx_d^2
     double cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
+    double cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
     double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
@@ -98,7 +99,11 @@ struct LeanMaps {
     CUtensorMap qbint;                      // base state, tile interior (Kutta RK3 / RK4)
     CUtensorMap opa, opb;                   // RA ; RB or the old RW (unpadded register arrays, tile interior)
 };
-void launch_rhs_stage_lean(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, cudaStream_t st);
+// wide: the 16-warp variant (tile 32 x 16; FAST + linear viscosity + at most the RA operand tile: see lean_wide_ok)
+void launch_rhs_stage_lean(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool wide, cudaStream_t st);
+bool lean_wide_ok(const KConst &kc);
+int lean_smem_wide_bytes(int s);
+#define CUDNS_LEAN_TY_WIDE 16
 int lean_smem_bytes(int s, bool linear_visc);
 int stage_tile_y();
 int stage_smem_bytes(int s, bool linear_visc);

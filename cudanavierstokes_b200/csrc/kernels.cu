@@ -641,45 +641,49 @@ __device__ __forceinline__ void atomic_max_pos(double *addr, double v) {
 }
 
 // deviceCalcDt (calc_stress.cu:140-160) as two maxima: min_p CFL/max(conv_p,visc_p) = CFL/max(max_p conv_p, max_p visc_p)
-__global__ void dt_reduce_kernel(KConst c, const double *q, double *out2) {
+__global__ void __launch_bounds__(256) dt_reduce_kernel(KConst c, const double *__restrict__ q, double *out2) {
     const Layout &L = c.L;
-    size_t N = (size_t)L.mx * L.my * L.mz;
+    const int nrows = L.my * L.mz;
     double mc = 0.0, mv = 0.0;
-    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
-        int i = (int)(n % L.mx); size_t rr = n / L.mx; int j = (int)(rr % L.my), k = (int)(rr / L.my);
-        size_t g = L.idx(i, j, k);
-        double r = q[g], u = q[L.vol + g], v = q[2 * L.vol + g], w = q[3 * L.vol + g], e = q[4 * L.vol + g];
-        double ien = e / r - 0.5 * (u * u + v * v + w * w);
-        double sos = sqrt(c.gam * (c.gam - 1) * ien);
-        double dx = c.dxv[i], d2x = dx * dx;
-        double conv = fmax((fabs(u) + sos) / dx, fmax((fabs(v) + sos) * c.d1[1], (fabs(w) + sos) * c.d1[2]));
-        double mu = visc_of(c, c.cvInv * ien);
-        double visc = fmax(mu / d2x, fmax(mu * c.d2[1], mu * c.d2[2]));
-        mc = fmax(mc, conv); mv = fmax(mv, visc);
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {            // one (j,k) row of the interior per iteration
+        const int j = row % L.my, k = row / L.my;
+        const double *p = q + L.idx(0, j, k);
+        for (int i = threadIdx.x; i < L.mx; i += blockDim.x) {
+            const double r = p[i], u = p[L.vol + i], v = p[2 * L.vol + i], w = p[3 * L.vol + i], e = p[4 * L.vol + i];
+            double ien = e / r - 0.5 * (u * u + v * v + w * w);
+            double sos = sqrt(c.gam * (c.gam - 1) * ien);
+            double dx = c.dxv[i], d2x = dx * dx;
+            double conv = fmax((fabs(u) + sos) / dx, fmax((fabs(v) + sos) * c.d1[1], (fabs(w) + sos) * c.d1[2]));
+            double mu = visc_of(c, c.cvInv * ien);
+            double visc = fmax(mu / d2x, fmax(mu * c.d2[1], mu * c.d2[2]));
+            mc = fmax(mc, conv); mv = fmax(mv, visc);
+        }
     }
     mc = warp_max(mc); mv = warp_max(mv);
     if ((threadIdx.x & 31) == 0) { atomic_max_pos(out2, mc); atomic_max_pos(out2 + 1, mv); }
 }
 void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st) {
     cudaMemsetAsync(out2, 0, 2 * sizeof(double), st);
-    dt_reduce_kernel<<<148 * 4, 256, 0, st>>>(kc, q, out2);
+    dt_reduce_kernel<<<148 * 8, 256, 0, st>>>(kc, q, out2);
 }
 
 // calcBulk / calcPressureGrad integrals (calc_stress.cu:98-120,162-201; cuda_math.cu:143-201):
 // out[0] = sum (u.u) w_avg, out[1] = sum rho w_int, out[2] = sum rho*w w_int, out[3] = sum rhoE w_int
 // with w_int = dxv[i]/d_dy/d_dz and w_avg = w_int/Lx/Ly/Lz.  Block partials are combined in a fixed order
 // by the last block (deterministic for a given launch shape).
-__global__ void bulk_reduce_kernel(KConst c, const double *q, double *out4, double *partial, unsigned int *counter) {
+__global__ void __launch_bounds__(256) bulk_reduce_kernel(KConst c, const double *__restrict__ q, double *out4, double *partial, unsigned int *counter) {
     const Layout &L = c.L;
-    size_t N = (size_t)L.mx * L.my * L.mz;
+    const int nrows = L.my * L.mz;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
-        int i = (int)(n % L.mx); size_t rr = n / L.mx; int j = (int)(rr % L.my), k = (int)(rr / L.my);
-        size_t g = L.idx(i, j, k);
-        double r = q[g], u = q[L.vol + g], v = q[2 * L.vol + g], w = q[3 * L.vol + g], e = q[4 * L.vol + g];
-        double wi = c.dxv[i] / c.d1[1] / c.d1[2];
-        s0 += (u * u + v * v + w * w) * wi / c.Lx / c.Ly / c.Lz;
-        s1 += r * wi; s2 += r * w * wi; s3 += e * wi;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int j = row % L.my, k = row / L.my;
+        const double *p = q + L.idx(0, j, k);
+        for (int i = threadIdx.x; i < L.mx; i += blockDim.x) {
+            const double r = p[i], u = p[L.vol + i], v = p[2 * L.vol + i], w = p[3 * L.vol + i], e = p[4 * L.vol + i];
+            double wi = c.dxv[i] / c.d1[1] / c.d1[2];
+            s0 += (u * u + v * v + w * w) * wi / c.Lx / c.Ly / c.Lz;
+            s1 += r * wi; s2 += r * w * wi; s3 += e * wi;
+        }
     }
     __shared__ double sh[4][8];
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
@@ -704,7 +708,7 @@ static double *g_bulk_partial[16] = {nullptr};
 static unsigned int *g_bulk_counter[16] = {nullptr};
 void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st) {
     int dev = 0; cudaGetDevice(&dev);
-    const int nb = 148 * 2;
+    const int nb = 148 * 4;
     if (!g_bulk_partial[dev]) {
         cudaMalloc(&g_bulk_partial[dev], 4 * nb * sizeof(double));
         cudaMalloc(&g_bulk_counter[dev], sizeof(unsigned int));

@@ -3,13 +3,14 @@
 #define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
 #include "stage_lean.inc"
 namespace cudns {
-void launch_lean_s1(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, cudaStream_t st) {
+void launch_lean_s1(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, bool wide, cudaStream_t st) {
     using namespace lean;
     switch (kc.v) {
-        case 1: launch_v<1, 1>(kc, p, c, maps, gen, st); break;
+        case 1: launch_v<1, 1>(kc, p, c, maps, gen, wide, st); break;
         default: break;
     }
 }
+int lean_smem_wide_s1() { return (int)lean::Cfg<1, 16, 8>::bytes; }
 int lean_smem_s1(bool linear_visc) {
     return (int)(linear_visc ? lean::Cfg<1, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<1, CUDNS_LEAN_TY_GENERAL, 9>::bytes);
 }

@@ -3,15 +3,16 @@
 #define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
 #include "stage_lean.inc"
 namespace cudns {
-void launch_lean_s3(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, cudaStream_t st) {
+void launch_lean_s3(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, bool wide, cudaStream_t st) {
     using namespace lean;
     switch (kc.v) {
-        case 1: launch_v<3, 1>(kc, p, c, maps, gen, st); break;
-        case 2: launch_v<3, 2>(kc, p, c, maps, gen, st); break;
-        case 3: launch_v<3, 3>(kc, p, c, maps, gen, st); break;
+        case 1: launch_v<3, 1>(kc, p, c, maps, gen, wide, st); break;
+        case 2: launch_v<3, 2>(kc, p, c, maps, gen, wide, st); break;
+        case 3: launch_v<3, 3>(kc, p, c, maps, gen, wide, st); break;
         default: break;
     }
 }
+int lean_smem_wide_s3() { return (int)lean::Cfg<3, 16, 8>::bytes; }
 int lean_smem_s3(bool linear_visc) {
     return (int)(linear_visc ? lean::Cfg<3, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<3, CUDNS_LEAN_TY_GENERAL, 9>::bytes);
 }

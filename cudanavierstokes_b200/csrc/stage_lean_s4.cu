@@ -3,16 +3,17 @@
 #define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
 #include "stage_lean.inc"
 namespace cudns {
-void launch_lean_s4(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, cudaStream_t st) {
+void launch_lean_s4(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, bool wide, cudaStream_t st) {
     using namespace lean;
     switch (kc.v) {
-        case 1: launch_v<4, 1>(kc, p, c, maps, gen, st); break;
-        case 2: launch_v<4, 2>(kc, p, c, maps, gen, st); break;
-        case 3: launch_v<4, 3>(kc, p, c, maps, gen, st); break;
-        case 4: launch_v<4, 4>(kc, p, c, maps, gen, st); break;
+        case 1: launch_v<4, 1>(kc, p, c, maps, gen, wide, st); break;
+        case 2: launch_v<4, 2>(kc, p, c, maps, gen, wide, st); break;
+        case 3: launch_v<4, 3>(kc, p, c, maps, gen, wide, st); break;
+        case 4: launch_v<4, 4>(kc, p, c, maps, gen, wide, st); break;
         default: break;
     }
 }
+int lean_smem_wide_s4() { return (int)lean::Cfg<4, 16, 8>::bytes; }
 int lean_smem_s4(bool linear_visc) {
     return (int)(linear_visc ? lean::Cfg<4, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<4, CUDNS_LEAN_TY_GENERAL, 9>::bytes);
 }

@@ -56,13 +56,13 @@ __device__ __forceinline__ double dwdz_edge(const KConst &c, const double *__res
     return dwdz;
 }
 
-template <int V>
+template <int V, bool GEN>
 __global__ void __launch_bounds__(NTT, 2)
 theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ q, double *__restrict__ theta, int zchunk) {
-    constexpr int R = 2 * V + 1;
     constexpr int VY = TYT + 2 * V;
-    __shared__ double su[2][TYT][UX];
-    __shared__ double sv[2][VY][TXT];
+    constexpr int SU = TYT * UX, SV = VY * TXT;           // doubles per buffer
+    __shared__ double su[2 * SU];                         // [2][TYT][UX]
+    __shared__ double sv[2 * SV];                         // [2][VY][TXT]
 
     const Layout &L = c.L;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -74,103 +74,99 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
     const int kfirst = -V + (int)blockIdx.z * zchunk;
     const int klast = min(kfirst + zchunk, L.mz + V);           // exclusive
     const int kglob_lo = -c.kstart, kglob_hi = c.mz_tot - c.kstart;
-    const bool bl = c.boundaryLayer != 0;
-    const bool perx = c.periodicX != 0;
+    const bool bl = GEN && c.boundaryLayer != 0;
+    const bool perx = !GEN || c.periodicX != 0;
     const bool xlo = !perx && i0 == 0, xhi = !perx && (i0 + TXT >= L.mx);
-    const double *__restrict__ U = q + L.vol, *__restrict__ Vv = q + 2 * L.vol, *__restrict__ W = q + 3 * L.vol;
     const size_t plane = L.plane;
 
-    // per-thread addresses (plane 0): own column, the x-halo cell and the y-halo row this thread also stages
-    const size_t g00 = L.idx(ic, jc, 0);
+    // this thread's column, the x-halo cell and the y-halo row it also stages: running pointers, one plane per iteration
+    const size_t g00 = L.idx(ic, jc, kfirst);
     const bool hx_on = tx < 2 * V && iny;
     const int hxc = tx < V ? GX - V + tx : GX + nxt + (tx - V);           // column in su
     const int hgi = i0 + hxc - GX;
     const bool hx_load = hx_on && (perx || (hgi >= 0 && hgi < L.mx));
-    const size_t ghx = L.idx(min(max(hgi, -GX), L.mx + GX - 1), jc, 0);
     const bool hy_on = ty < 2 * V && inx;
     const int hyr = ty < V ? ty : V + nyt + (ty - V);                     // row in sv
-    const size_t ghy = L.idx(ic, j0 + hyr - V, 0);
-    const double xpi = c.nonUniformX ? c.xp[ic] : 1.0;
+    const double *pu = q + L.vol + g00, *pv = q + 2 * L.vol + g00, *pw = q + 3 * L.vol + g00 + (size_t)V * plane;
+    const double *puh = q + L.vol + L.idx(min(max(hgi, -GX), L.mx + GX - 1), jc, kfirst);
+    const double *pvh = q + 2 * L.vol + L.idx(ic, j0 + hyr - V, kfirst);
+    double *pt = theta + g00;
+    const double xpi = (GEN && c.nonUniformX) ? c.xp[ic] : 1.0;
+    // shared-memory slots (doubles, buffer 0)
+    const int o_u = ty * UX + GX + tx, o_uh = ty * UX + hxc, o_v = (V + ty) * TXT + tx, o_vh = hyr * TXT + tx;
+    // image flags: 1 x-low, 2 x-high, 4 y-low, 8 y-high (perBCx / perBCy, boundary.h:38-46)
+    const unsigned img = ((perx && i < V) ? 1u : 0u) | ((perx && i >= L.mx - V) ? 2u : 0u) | ((j < V) ? 4u : 0u) | ((j >= L.my - V) ? 8u : 0u);
 
-    double wr[R];
+    double wr[2 * V + 1];                                 // wr[V + l] = w of plane k+l
 #pragma unroll
-    for (int r = 0; r < R; r++) wr[r] = 0.0;
-    // prologue: w of planes kfirst-V .. kfirst+V-1 into ring positions 0 .. 2V-1 (position of plane kfirst+m-V is m)
-#pragma unroll
-    for (int m = 0; m < 2 * V; m++) wr[m] = W[g00 + (ptrdiff_t)(kfirst + m - V) * (ptrdiff_t)plane];
+    for (int m = 0; m < 2 * V; m++) wr[m + 1] = pw[(ptrdiff_t)(m - 2 * V) * (ptrdiff_t)plane];
     // staged values of the next plane
-    double un, vn, uhn = 0.0, vhn = 0.0, wn;
-    {
-        const ptrdiff_t off = (ptrdiff_t)kfirst * (ptrdiff_t)plane;
-        un = U[g00 + off]; vn = Vv[g00 + off]; wn = W[g00 + off + (ptrdiff_t)V * (ptrdiff_t)plane];
-        if (hx_load) uhn = U[ghx + off];
-        if (hy_on) vhn = Vv[ghy + off];
-    }
+    double un = *pu, vn = *pv, wn = *pw, uhn = 0.0, vhn = 0.0;
+    if (hx_load) uhn = *puh;
+    if (hy_on) vhn = *pvh;
 
-    int buf = 0;
-    {
-        for (int k = kfirst; k < klast; k++) {
-            // wr[V + l] = w of plane k+l
-            wr[2 * V] = wn;
-            if (active) { su[buf][ty][GX + tx] = un; sv[buf][V + ty][tx] = vn; }
-            if (hx_load) su[buf][ty][hxc] = uhn;
-            if (hy_on) sv[buf][hyr][tx] = vhn;
-            __syncthreads();
-            if (k + 1 < klast) {                         // stage plane k+1 (consumed at the top of the next iteration)
-                const ptrdiff_t off = (ptrdiff_t)(k + 1) * (ptrdiff_t)plane;
-                un = U[g00 + off]; vn = Vv[g00 + off]; wn = W[g00 + off + (ptrdiff_t)V * (ptrdiff_t)plane];
-                if (hx_load) uhn = U[ghx + off];
-                if (hy_on) vhn = Vv[ghy + off];
-            }
-            const bool outside = bl && (k < kglob_lo || k >= kglob_hi);    // ghost theta is extrapolated by the stage kernel
+    int boff_u = 0, boff_v = 0;
+    for (int k = kfirst; k < klast; k++) {
+#pragma unroll
+        for (int m = 0; m < 2 * V; m++) wr[m] = wr[m + 1];
+        wr[2 * V] = wn;
+        if (active) { su[boff_u + o_u] = un; sv[boff_v + o_v] = vn; }
+        if (hx_load) su[boff_u + o_uh] = uhn;
+        if (hy_on) sv[boff_v + o_vh] = vhn;
+        __syncthreads();
+        pu += plane; pv += plane; pw += plane; puh += plane; pvh += plane;
+        if (k + 1 < klast) {                             // stage plane k+1 (consumed at the top of the next iteration)
+            un = *pu; vn = *pv; wn = *pw;
+            if (hx_load) uhn = *puh;
+            if (hy_on) vhn = *pvh;
+        }
+        const bool outside = bl && (k < kglob_lo || k >= kglob_hi);    // ghost theta is extrapolated by the stage kernel
+        if constexpr (GEN) {
             if (xlo || xhi) {
                 // BCxderVel: wall (anti-mirror about the face, + blowing/suction) / node extrapolation at the free stream
                 if (hx_on && !hx_load && !outside) {
+                    const double *row = su + boff_u + ty * UX;
                     double val;
                     if (tx < V) {
                         const int gq = V - tx;                            // ghost -gq
-                        val = -su[buf][ty][GX + gq - 1];
-                        double pv;
-                        if (bl && c.perturbed && perturb_theta(c, j, k + c.kstart, pv)) val = pv;
+                        val = -row[GX + gq - 1];
+                        double pv2;
+                        if (bl && c.perturbed && perturb_theta(c, j, k + c.kstart, pv2)) val = pv2;
                     } else {
                         const int gq = tx - V + 1, last = GX + nxt - 1;
-                        val = bl ? 2.0 * su[buf][ty][last] - su[buf][ty][last - gq] : -su[buf][ty][last - gq + 1];
+                        val = bl ? 2.0 * row[last] - row[last - gq] : -row[last - gq + 1];
                     }
-                    su[buf][ty][hxc] = val;
+                    su[boff_u + o_uh] = val;
                 }
                 __syncthreads();
             }
-            if (active && !outside) {
-                double dudx = 0.0, dvdy = 0.0, dwdz = 0.0;
-                const double *ur = &su[buf][ty][GX + tx];
-                const double *vr = &sv[buf][V + ty][tx];
-#pragma unroll
-                for (int l = 1; l <= V; l++) {
-                    dudx = fma(c.c1[0][l], ur[l] - ur[-l], dudx);
-                    dvdy = fma(c.c1[1][l], vr[l * TXT] - vr[-l * TXT], dvdy);
-                }
-                if (bl && (k - kglob_lo < V || kglob_hi - 1 - k < V)) {
-                    // botBCzExt / topBCzExt (boundary.h:154-160): node extrapolation of w past the global z boundaries
-                    dwdz = dwdz_edge<V>(c, W, ic, jc, k, kglob_lo, kglob_hi);
-                } else {
-#pragma unroll
-                    for (int l = 1; l <= V; l++) dwdz = fma(c.c1[2][l], wr[V + l] - wr[V - l], dwdz);
-                }
-                const double th = fma(dudx, xpi, dvdy) + dwdz;
-                double *t = theta + g00 + (ptrdiff_t)k * (ptrdiff_t)plane;
-                *t = th;
-                // periodic images in x / y (cross-shaped ghosts only): perBCx / perBCy, boundary.h:38-46
-                if (perx) {
-                    if (i < V) t[L.mx] = th;
-                    if (i >= L.mx - V) t[-(ptrdiff_t)L.mx] = th;
-                }
-                if (j < V) t[(size_t)L.my * L.px] = th;
-                if (j >= L.my - V) t[-(ptrdiff_t)((size_t)L.my * L.px)] = th;
-            }
-            buf ^= 1;
-#pragma unroll
-            for (int m = 0; m < 2 * V; m++) wr[m] = wr[m + 1];
         }
+        if (active && !outside) {
+            double dudx = 0.0, dvdy = 0.0, dwdz = 0.0;
+            const double *ur = su + boff_u + o_u;
+            const double *vr = sv + boff_v + o_v;
+#pragma unroll
+            for (int l = 1; l <= V; l++) {
+                dudx = fma(c.c1[0][l], ur[l] - ur[-l], dudx);
+                dvdy = fma(c.c1[1][l], vr[l * TXT] - vr[-l * TXT], dvdy);
+            }
+            if (GEN && bl && (k - kglob_lo < V || kglob_hi - 1 - k < V)) {
+                dwdz = dwdz_edge<V>(c, q + 3 * L.vol, ic, jc, k, kglob_lo, kglob_hi);
+            } else {
+#pragma unroll
+                for (int l = 1; l <= V; l++) dwdz = fma(c.c1[2][l], wr[V + l] - wr[V - l], dwdz);
+            }
+            const double th = (GEN ? fma(dudx, xpi, dvdy) : dudx + dvdy) + dwdz;
+            *pt = th;
+            if (img) {
+                if (img & 1u) pt[L.mx] = th;
+                if (img & 2u) pt[-(ptrdiff_t)L.mx] = th;
+                if (img & 4u) pt[(size_t)L.my * L.px] = th;
+                if (img & 8u) pt[-(ptrdiff_t)((size_t)L.my * L.px)] = th;
+            }
+        }
+        pt += plane;
+        boff_u ^= SU; boff_v ^= SV;
     }
 }
 
@@ -185,12 +181,18 @@ void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaSt
     int zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);
+    const bool gen = !(kc.periodicX && !kc.nonUniformX && !kc.boundaryLayer);
+#define CUDNS_THETA_CASE(VV)                                                                        \
+    case VV:                                                                                        \
+        if (gen) theta_march_kernel<VV, true><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);          \
+        else theta_march_kernel<VV, false><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);             \
+        break;
     switch (kc.v) {
-        case 1: theta_march_kernel<1><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk); break;
-        case 2: theta_march_kernel<2><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk); break;
-        case 3: theta_march_kernel<3><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk); break;
-        default: theta_march_kernel<4><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk); break;
+        CUDNS_THETA_CASE(1) CUDNS_THETA_CASE(2) CUDNS_THETA_CASE(3)
+        default: if (gen) theta_march_kernel<4, true><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);
+                 else theta_march_kernel<4, false><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);
     }
+#undef CUDNS_THETA_CASE
 }
 
 }  // namespace cudns

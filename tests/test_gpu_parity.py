@@ -105,6 +105,20 @@ def test_tgv32_steps_vs_oracle(scheme):
     assert abs(b1[0] - a1[0]) < 1e-13
 
 
+@pytest.mark.parametrize("sv", [(4, 4), (3, 2), (2, 2)])
+def test_narrow_tile_variant_of_the_stage_kernel(sv, monkeypatch):
+    """the periodic / linear-viscosity Taylor-Green set-up normally runs the 16-warp tile of the stage kernel (ring without p);
+    CUDNS_WIDE=0 selects the 12-warp tile with the full ring -- both must match the oracle"""
+    monkeypatch.setenv("CUDNS_WIDE", "0")
+    op = ob.params_tgv(32, sv[0], stencilVisc=sv[1], mz=40)
+    o, s, grid = make_pair(op)
+    o.init_chit(); s.set_state(o.state())
+    _rhs_check(o, s)
+    o.run(11); s.advance(11)
+    errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+    assert max(errs) < TOL, errs
+
+
 def test_dt_and_bulk():
     op = ob.params_tgv(24, 3)
     o, s, grid = make_pair(op)
