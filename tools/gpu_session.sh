@@ -12,5 +12,5 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
    python bench.py --n 256 --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:stage_kernel -s 6 -c 1 -f -o gpurun_out/${TAG}_stage_full \
-   python tools/quick_perf.py 256,4,4 > gpurun_out/${TAG}_stage_full.log 2>&1
+   python tools/quick_perf.py 512,4,4 > gpurun_out/${TAG}_stage_full.log 2>&1
 ls -la gpurun_out | tail -20
