@@ -59,6 +59,12 @@ struct cudns_solver {
     StageMaps wmaps[3];          // tile of the wide (16-warp) lean kernel
     CUtensorMap wrmap[2];
     bool wide;                   // the wide variant applies to this configuration (CUDNS_WIDE=0 disables it)
+    bool fast;                   // ... and is served by the fourth-generation kernel (stage_fast.cu; CUDNS_WIDE=1: the lean wide variant)
+    int fast_ty;                 // its tile rows: 8 (two CTAs per SM, default) or 16 (CUDNS_FAST_TY=16)
+    int nfb;                     // padded fields per state buffer: 5, or FAST_NFB = 8 (+ H, T, theta) when the fast kernel applies
+    FastMaps fmaps[3];           // its TMA descriptors per state buffer (opa is patched per launch)
+    CUtensorMap frmap[2];        // R1 / R2 with its tile
+    bool aux_valid[3];           // H, T of state[b] (ghosts included) match its (rho,u,v,w,rho*E)
     int stage_gen;               // 3: lean kernel (default); CUDNS_STAGE=tmem -> 2, CUDNS_STAGE=smem -> 1 (A/B timing only)
 };
 
@@ -137,11 +143,19 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     S->N = (size_t)mx * my * mzl;
     CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     S->nstate = (p->lowStorage && !p->rk4) ? 2 : 3;
-    S->block_doubles = (size_t)S->nstate * 5 * L.vol;
+    {   // the fourth-generation stage kernel (stage_fast.cu) applies to the periodic / uniform / linear-viscosity set-ups; its state
+        // buffers carry three more padded fields (H, T, theta).  CUDNS_WIDE=0 / 1 select the older kernels (A/B timing)
+        const char *we = getenv("CUDNS_WIDE"), *fe = getenv("CUDNS_FAST_TY");
+        S->fast_ty = (fe && std::string(fe) == "16") ? 16 : 8;
+        S->fast = p->viscexp == 1.0 && p->periodicX && !p->nonUniformX && !p->boundaryLayer && !(we && (std::string(we) == "0" || std::string(we) == "1")) &&
+                  (size_t)fast_smem_bytes(s, S->fast_ty) <= prop.sharedMemPerBlockOptin;
+        S->nfb = S->fast ? FAST_NFB : 5;
+    }
+    S->block_doubles = (size_t)S->nstate * S->nfb * L.vol;
     S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
     if ((rc = dmalloc(S, &S->block, S->block_doubles + 32))) { cudns_destroy(S); return rc; }
     CK(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(double), S->st));
-    for (int b = 0; b < S->nstate; b++) S->state[b] = S->block + (size_t)b * 5 * L.vol;
+    for (int b = 0; b < S->nstate; b++) S->state[b] = S->block + (size_t)b * S->nfb * L.vol;
     if ((rc = dmalloc(S, &S->theta, L.vol))) { cudns_destroy(S); return rc; }
     CK(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
     if ((rc = dmalloc(S, &S->R1, 5 * S->N))) { cudns_destroy(S); return rc; }
@@ -177,6 +191,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             kc.c1t[d][l] = kc.c1[d][l] / 3.0;
         }
         if (d == 2) for (int l = 0; l <= MAXS; l++) kc.cfzp[l] = -kc.cP[2][l] * (1.f / (p->gam * p->Ma * p->Ma));
+        for (int l = 0; l <= MAXS; l++) kc.cfp[d][l] = -kc.cP[d][l] * (1.f / (p->gam * p->Ma * p->Ma));
         kc.c20sum += kc.c2[d][0];
     }
     kc.gam = p->gam;
@@ -241,6 +256,18 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         if ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty)))) { cudns_destroy(S); return rc; }
         const char *we = getenv("CUDNS_WIDE");
         S->wide = lean_wide_ok(kc) && !(we && std::string(we) == "0") && (size_t)lean_smem_wide_bytes(s) <= prop.sharedMemPerBlockOptin;
+        if (S->fast) {
+            const int fty = S->fast_ty, FYb = fty + 2 * s;
+            for (int b = 0; b < S->nstate; b++) {
+                double *q = S->state[b];
+                if ((rc = make_map(&S->fmaps[b].q4box, L, q, 4, CXb, FYb)) || (rc = make_map(&S->fmaps[b].a3box, L, q + 5 * L.vol, 3, CXb, FYb)) ||
+                    (rc = make_map(&S->fmaps[b].q4int, L, q, 4, 32, fty)) || (rc = make_map(&S->fmaps[b].a3int, L, q + 5 * L.vol, 3, 32, fty)) ||
+                    (rc = make_map(&S->fmaps[b].eint, L, q + 4 * L.vol, 1, 32, fty))) {
+                    cudns_destroy(S); return rc;
+                }
+            }
+            if ((rc = make_rmap(&S->frmap[0], L, S->R1, fty)) || (S->R2 && (rc = make_rmap(&S->frmap[1], L, S->R2, fty)))) { cudns_destroy(S); return rc; }
+        }
         if (S->wide) {
             const int wty = CUDNS_LEAN_TY_WIDE, WYb = wty + 2 * s;
             for (int b = 0; b < S->nstate; b++) {
@@ -378,6 +405,7 @@ int cudns_set_state_device(cudns_handle S, const double *d_r, const double *d_u,
     CK(cudaSetDevice(S->P.device));
     const double *src[5] = {d_r, d_u, d_v, d_w, d_e};
     S->cur = 0;
+    for (int b = 0; b < 3; b++) S->aux_valid[b] = false;
     launch_pad(S->kc, src, S->state[0], S->st);
     launch_fill_xy(S->kc, S->state[0], 5, S->st);
     S->launches += 2;
@@ -464,6 +492,15 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
     else {
         // the wide variant stages one operand tile only (RA): every low-storage RK3 stage and the test path qualify
         const bool wide = S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
+        if (wide && S->fast) {
+            // 8-field buffers: theta of the input state is its field 7 (run_stage put it there), H and T are rebuilt first when the
+            // buffer was not written by this kernel
+            if (!S->aux_valid[in]) { launch_derive_aux(S->kc, S->state[in], S->st); S->launches++; S->aux_valid[in] = true; }
+            FastMaps m = S->fmaps[in];
+            m.opa = (p.RA == S->R2) ? S->frmap[1] : S->frmap[0];
+            launch_rhs_stage_fast(S->kc, p, c, m, S->fast_ty, S->st);
+            return;
+        }
         const StageMaps *sm = wide ? S->wmaps : S->lmaps;
         const CUtensorMap *rm = wide ? S->wrmap : S->rmap;
         LeanMaps m;
@@ -476,6 +513,11 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
     }
 }
 
+// will launch_stage_any serve this stage with the fast kernel?
+static bool stage_is_fast(const cudns_solver *S, const StagePtrs &p, const StageCoef &c) {
+    return S->stage_gen == 3 && S->fast && S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
+}
+
 // does this solver's stage kernel write the z ghost planes itself (lean kernel; on one device always, across devices once
 // the peer blocks are mapped)?
 static bool inkernel_ghosts(const cudns_solver *S) { return S->stage_gen == 3 && (S->P.nranks == 1 || S->connected); }
@@ -484,7 +526,7 @@ static bool inkernel_ghosts(const cudns_solver *S) { return S->stage_gen == 3 &&
 static void ghost_targets(cudns_solver *S, int out, StagePtrs &p) {
     p.qout_lo = nullptr; p.qout_hi = nullptr;
     if (!inkernel_ghosts(S)) return;
-    const size_t off = (size_t)out * 5 * S->L.vol;
+    const size_t off = (size_t)out * S->nfb * S->L.vol;
     const bool bl = S->P.boundaryLayer != 0;                  // z is not periodic: the global bottom / top have no neighbour
     if (S->P.nranks == 1) { if (!bl) { p.qout_lo = S->state[out]; p.qout_hi = S->state[out]; } return; }
     if (!(bl && S->P.rank == 0)) p.qout_lo = S->peer_lo + off;
@@ -509,10 +551,12 @@ static void handshake(cudns_solver *S) {
 // one RHS evaluation + register update: K = RHS(state[in]); see StageCoef
 static int run_stage(cudns_solver *S, int in, int base, int out, const double *RA, const double *RB, double *RW,
                      const StageCoef &c, double *rhs_out) {
-    launch_theta(S->kc, S->state[in], S->theta, S->st);
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
     p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
+    const bool fast = stage_is_fast(S, p, c);
+    if (fast) p.theta = S->state[in] + 7 * S->L.vol;            // 8-field buffers: theta travels with the state it belongs to
+    launch_theta(S->kc, S->state[in], const_cast<double *>(p.theta), S->st);
     ghost_targets(S, out, p);
     if (rhs_out) { p.qout_lo = nullptr; p.qout_hi = nullptr; }
     launch_stage_any(S, p, c, in, base);
@@ -520,6 +564,9 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
     if (!rhs_out) {
+        // H, T of the new state: written by the fast kernel together with the state (ghost planes included when it stores them
+        // itself); stale after any other kernel or after a separate ghost exchange
+        S->aux_valid[out] = fast && inkernel_ghosts(S);
         if (inkernel_ghosts(S)) handshake(S);
         else { int rc = fill_z_ghosts(S, S->state[out]); if (rc) return rc; }
         S->stages++;
@@ -688,12 +735,18 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
     StageCoef c = {0.0, 0, 0, 0, 1};     // cN = 0: the state is copied through unchanged, so reps do not drift
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(e0, S->st));
-        launch_theta(S->kc, S->state[a], S->theta, S->st);
-        CK(cudaEventRecord(e1, S->st));
         StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
         p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
+        const bool fast = stage_is_fast(S, p, c);
+        if (fast) {
+            p.theta = S->state[a] + 7 * S->L.vol;
+            if (!S->aux_valid[a]) { launch_derive_aux(S->kc, S->state[a], S->st); S->aux_valid[a] = true; }
+        }
+        launch_theta(S->kc, S->state[a], const_cast<double *>(p.theta), S->st);
+        CK(cudaEventRecord(e1, S->st));
         ghost_targets(S, b, p);
         launch_stage_any(S, p, c, a, a);
+        S->aux_valid[b] = false;                          // a scratch copy of the state, never advanced from
         CK(cudaEventRecord(e2, S->st));
         if (inkernel_ghosts(S)) handshake(S);
         else { int rc = fill_z_ghosts(S, S->state[b]); if (rc) return rc; }

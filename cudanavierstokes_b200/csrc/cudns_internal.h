@@ -44,6 +44,7 @@ struct KConst {
     // c1t = a_l/(3 dx_d) (viscous order), c20sum = sum_d b_0/dx_d^2
     double cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
     double cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
+    double cfp[3][MAXS + 1];     // -a_l Rgas / dx_d: pressure gradient from rho*T in every direction (fast variant)
     double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
@@ -102,6 +103,18 @@ struct LeanMaps {
 // wide: the 16-warp variant (tile 32 x 16; FAST + linear viscosity + at most the RA operand tile: see lean_wide_ok)
 void launch_rhs_stage_lean(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool wide, cudaStream_t st);
 bool lean_wide_ok(const KConst &kc);
+// fourth-generation kernel (stage_fast.cu): same preconditions and TMA descriptors as the wide lean variant
+// (stage_fast.cu).  Its state buffers carry 8 padded fields: rho,u,v,w,rho*E, H,T (written with the state) and theta.
+constexpr int FAST_NFB = 8;
+struct FastMaps {
+    CUtensorMap q4box, a3box;               // halo'd tile of (rho,u,v,w) and of (H,T,theta)
+    CUtensorMap q4int, a3int;               // tile interior of the same (plane S ahead, for the z ring)
+    CUtensorMap eint;                       // rho*E, tile interior
+    CUtensorMap opa;                        // RA (unpadded register array, tile interior)
+};
+void launch_rhs_stage_fast(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, int ty, cudaStream_t st);
+void launch_derive_aux(const KConst &kc, double *q8, cudaStream_t st);
+int fast_smem_bytes(int s, int ty);
 int lean_smem_wide_bytes(int s);
 #define CUDNS_LEAN_TY_WIDE 16
 int lean_smem_bytes(int s, bool linear_visc);
