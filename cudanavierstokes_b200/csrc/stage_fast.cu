@@ -26,6 +26,13 @@
 #define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
 #include "stage_lean.inc"
 
+#ifndef FAST_L2_HINTS
+#define FAST_L2_HINTS 0       // 1: L2 eviction hints on the TMA loads + streaming stores (measured: no gain, 143 vs 149 B/pt read)
+#endif
+#ifndef FAST_ONESIDED
+#define FAST_ONESIDED 0       // 1: one neighbour at a time (fewer registers, one more FP64 instruction per neighbour pair)
+#endif
+
 namespace cudns {
 namespace fast {
 
@@ -68,6 +75,19 @@ __device__ __forceinline__ void eos_ht(const KConst &c, double r, double rinv, d
     const double t = c.cvInv * en;
     const double p = r * c.Rgas * t;
     H = (e + p) * rinv; T = t;
+}
+
+// TMA loads with an L2 eviction hint.  The stage streams ~250 B per point through L2 but re-reads only the tile interior it
+// loaded S planes ahead for the ring (as part of the halo'd plane): that window survives in L2 only if everything else -- the
+// halo'd planes themselves, rho*E, the Runge-Kutta operand, all stores -- is marked evict-first
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull, L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const CUtensorMap *map, uint32_t mbar, int c0, int c1, int c2, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"((uint64_t)map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 
 // tensor-memory load of ring slots, split into issue and wait so that independent work can sit in between; the wait takes the
@@ -119,6 +139,16 @@ __constant__ uint32_t ring_off[4][18] = {
 // thread index that the compiler cannot hoist out of the plane loop (everything derived from it is rebuilt where it is used
 // instead of living in -- or being spilled from -- a register across the stencil sums)
 __device__ __forceinline__ int tid_now() { int t; asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t)); return t; }
+__device__ __forceinline__ int ctaid_z_now() { int t; asm volatile("mov.u32 %0, %%ctaid.z;" : "=r"(t)); return t; }
+__device__ __forceinline__ uint32_t lds_u32_now(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+__device__ __forceinline__ void st_out(double *p, double v) {
+#if FAST_L2_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // running sums of one point
 struct Acc {
@@ -155,13 +185,38 @@ __device__ __forceinline__ void pair_step(const KConst &c, const int l, const do
         A.lapu[D] = fma(c.c1t[D][l], Pn[FD] - Mn[FD], A.lapu[D]);
     }
 }
+// one neighbour of direction D at offset +l (PLUS) or -l: the same sums, one side at a time (one more FP64 instruction per pair,
+// half the registers for neighbour values)
+template <int D, int V, bool PLUS>
+__device__ __forceinline__ void side_step(const KConst &c, const int l, const double (&C)[NF], const double (&Nq)[NF], Acc &A, double &aM) {
+    const double cC = c.cf[D][l][0];
+    const double cu = cC * C[FU + D];
+    const double Af = (C[FR] + Nq[FR]) * fma(cC, Nq[FU + D], cu);
+    const double pn = Nq[FR] * Nq[FT];
+    const double sA = PLUS ? Af : -Af;
+    aM += sA;
+    A.r[1] = fma(sA, Nq[FU], A.r[1]); A.r[2] = fma(sA, Nq[FV], A.r[2]); A.r[3] = fma(sA, Nq[FW], A.r[3]); A.r[4] = fma(sA, Nq[FH], A.r[4]);
+    A.r[1 + D] = fma(PLUS ? c.cfp[D][l] : -c.cfp[D][l], pn, A.r[1 + D]);
+    if (l <= V) {
+        const double k1 = PLUS ? c.cf[D][l][2] : -c.cf[D][l][2], k2 = c.cf[D][l][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            A.g[D][m] = fma(k1, Nq[FU + m], A.g[D][m]);
+            A.lapu[m] = fma(k2, Nq[FU + m], A.lapu[m]);
+        }
+        A.dT[D] = fma(k1, Nq[FT], A.dT[D]);
+        A.lapT = fma(k2, Nq[FT], A.lapT);
+        A.lapu[D] = fma(PLUS ? c.c1t[D][l] : -c.c1t[D][l], Nq[FD], A.lapu[D]);
+    }
+}
 // the direction is complete: central values times its mass-flux sum
 __device__ __forceinline__ void close_dir(const double (&C)[NF], Acc &A, const double aM) {
     A.r[0] = fma(2.0, aM, A.r[0]);
     A.r[1] = fma(C[FU], aM, A.r[1]); A.r[2] = fma(C[FV], aM, A.r[2]); A.r[3] = fma(C[FW], aM, A.r[3]); A.r[4] = fma(C[FH], aM, A.r[4]);
 }
 
-template <int S, int V, int TY>
+// MODE 0: write the right-hand side only (test path); 1: Runge-Kutta update without an RA operand; 2: with RA
+template <int S, int V, int TY, int MODE>
 __global__ void __launch_bounds__(TX * TY, TY == 16 ? 1 : 2)
 stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs P, const __grid_constant__ StageCoef sc, int zchunk,
              const __grid_constant__ FastMaps tm) {
@@ -178,9 +233,8 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     const int ty = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp == tile row (warp-uniform for the compiler)
     const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
     const int kbeg = blockIdx.z * zchunk;
-    const int kend = min(kbeg + zchunk, L.mz);
-    const bool do_update = !P.rhs_out;
-    const bool useA = do_update && P.RA != nullptr;
+    constexpr bool do_update = MODE != 0, useA = MODE == 2;
+    auto kend_now = [&]() { return min((ctaid_z_now() + 1) * zchunk, c.L.mz); };
 
     // mb_full[b]: the TMA loads of a plane bundle into buffer b have landed; mb_free: every warp has taken its ring values out of intb
     const uint32_t mb_full0 = smem_u32(mbar_p), mb_free = mb_full0 + 16;
@@ -194,7 +248,8 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem0 = *tmem_holder;
-    const uint32_t tbase = tmem0 + ((uint32_t)(32 * (ty & 3)) << 16) + (uint32_t)((ty >> 2) * G::COLS_THREAD);
+    auto tbase_of = [&](int wy) { return lds_u32_now(smem_u32(tmem_holder)) + ((uint32_t)(32 * (wy & 3)) << 16) + (uint32_t)((wy >> 2) * G::COLS_THREAD); };
+    const uint32_t tbase = tbase_of(ty);
     auto tslot = [&](int kk) -> uint32_t { return tbase + (uint32_t)(((kk + 16 * R) % R) * G::COLS_SLOT); };
 
     const uint32_t s_base = smem_u32(smem), s_int = smem_u32(intb);
@@ -203,12 +258,21 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         const uint32_t mb = mb_full0 + 8 * b;
         const uint32_t s_box = s_base + (uint32_t)(b * G::BUF_D * 8), s_e = s_box + (uint32_t)(G::BOX_D * 8), s_op = s_e + (uint32_t)(G::E_D * 8);
         mbar_expect_tx(mb, (uint32_t)((G::BOX_D + G::E_D + (useA ? G::OP_D : 0) + G::INT_D) * sizeof(double)));
+#if FAST_L2_HINTS
+        tma_load_4d_hint(s_box, &tm.q4box, mb, i0, j0 + L.gy - S, k + L.gz, 0, L2_EVICT_FIRST);
+        tma_load_4d_hint(s_box + 4 * CSZ * 8, &tm.a3box, mb, i0, j0 + L.gy - S, k + L.gz, 0, L2_EVICT_FIRST);
+        tma_load_4d_hint(s_int, &tm.q4int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0, L2_EVICT_LAST);
+        tma_load_4d_hint(s_int + 4 * NT * 8, &tm.a3int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0, L2_EVICT_LAST);
+        tma_load_3d_hint(s_e, &tm.eint, mb, i0 + GX, j0 + L.gy, k + L.gz, L2_EVICT_FIRST);
+        if (useA) tma_load_4d_hint(s_op, &tm.opa, mb, i0, j0, k, 0, L2_EVICT_FIRST);
+#else
         tma_load_4d(s_box, &tm.q4box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
         tma_load_4d(s_box + 4 * CSZ * 8, &tm.a3box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
         tma_load_4d(s_int, &tm.q4int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0);
         tma_load_4d(s_int + 4 * NT * 8, &tm.a3int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0);
         tma_load_3d(s_e, &tm.eint, mb, i0 + GX, j0 + L.gy, k + L.gz);
         if (useA) tma_load_4d(s_op, &tm.opa, mb, i0, j0, k, 0);
+#endif
     };
 
     // ---- prologue: planes kbeg-S .. kbeg+S-1 into the ring, two batches of S planes through the (still unused) buffers
@@ -233,14 +297,18 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     // ring slot of plane k-S+n: column offset ring_off[s0 + n] with s0 = (k-S) mod R
     int s0 = (kbeg - S + 16 * R) % R;
     const size_t N = (size_t)L.mx * L.my * L.mz;
-    for (int k = kbeg; k < kend; k++, s0 = (s0 + 1 == R) ? 0 : s0 + 1) {
-        const int kk = k - kbeg;
+    for (int k = kbeg; k < kend_now(); k++, s0 = (s0 + 1 == R) ? 0 : s0 + 1) {
+        // everything that depends on the thread index is rebuilt here and again before the update instead of being kept in (or
+        // spilled from) registers across the stencil sums
+        const int tn = tid_now();
+        const int tx = tn & 31, ty = tn >> 5;
+        const int kk = k - ctaid_z_now() * zchunk;
         const int b = kk & 1;
         const double *box = smem + (size_t)b * G::BUF_D;
+        const uint32_t tbase = tbase_of(__shfl_sync(0xffffffffu, ty, 0));
         uint32_t zs[R];
 #pragma unroll
         for (int n = 0; n < R; n++) zs[n] = tbase + ring_off[S - 1][s0 + n];
-        const int tx = tid_now() & 31;
         const int own = (ty + S) * CX + (tx + GX);
         // the first buffer's barrier has already completed two phases in the prologue: the parities line up (phase 2 -> parity 0)
         mbar_wait(mb_full0 + 8 * b, (uint32_t)(kk >> 1) & 1u);
@@ -268,17 +336,22 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             double aM = 0.0;
 #pragma unroll
             for (int l = 1; l <= S; l++) {
+#if FAST_ONESIDED
+                { Slot sp; slot_issue(zs[S + l], sp); double Nq[NF]; slot_wait(sp, Nq); side_step<2, V, true>(c, l, C, Nq, A, aM); }
+                { Slot sm; slot_issue(zs[S - l], sm); double Nq[NF]; slot_wait(sm, Nq); side_step<2, V, false>(c, l, C, Nq, A, aM); }
+#else
                 Slot sp, sm;
                 slot_issue(zs[S + l], sp); slot_issue(zs[S - l], sm);
                 double Pn[NF], Mn[NF];
                 slot_wait2(sp, sm, Pn, Mn);
                 pair_step<2, V>(c, l, C, Pn, Mn, A, aM);
+#endif
             }
             close_dir(C, A, aM);
         }
         // ---- the elected thread: once every warp has emptied intb (which also means it is done with plane k-1 and its buffer),
         // the loads of plane k+1 go out; they have the x / y directions, the assembly and the update of this plane to land
-        if (ty == 0 && tx == 0 && k + 1 < kend) {
+        if (tn == 0 && k + 1 < kend_now()) {
             mbar_wait(mb_free, (uint32_t)kk & 1u);
             issue_bundle(k + 1, b ^ 1);
         }
@@ -292,6 +365,17 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
                 double aM = 0.0;
 #pragma unroll
                 for (int l = 1; l <= S; l++) {
+#if FAST_ONESIDED
+#pragma unroll
+                    for (int sgn = 0; sgn < 2; sgn++) {
+                        double Nq[NF];
+                        const int off = sgn ? -l * dstr : l * dstr;
+#pragma unroll
+                        for (int f = 0; f < NF; f++) Nq[f] = (f < FD || l <= V) ? pc[f * CSZ + off] : 0.0;
+                        if (d == 0) { if (sgn) side_step<0, V, false>(c, l, C, Nq, A, aM); else side_step<0, V, true>(c, l, C, Nq, A, aM); }
+                        else { if (sgn) side_step<1, V, false>(c, l, C, Nq, A, aM); else side_step<1, V, true>(c, l, C, Nq, A, aM); }
+                    }
+#else
                     double Pn[NF], Mn[NF];
 #pragma unroll
                     for (int f = 0; f < NF; f++) {
@@ -299,6 +383,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
                         else { Pn[f] = 0.0; Mn[f] = 0.0; }
                     }
                     if (d == 0) pair_step<0, V>(c, l, C, Pn, Mn, A, aM); else pair_step<1, V>(c, l, C, Pn, Mn, A, aM);
+#endif
                 }
                 close_dir(C, A, aM);
             }
@@ -335,12 +420,12 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         if (c.forcing) { const double fz = *c.dpdz; rhs[3] += fz; rhs[4] = fma(fz, C[FW], rhs[4]); }      // cuda_rhs.cu:392-393
         // this thread's point: flags (1 active, 2/4 periodic x images low/high, 8/16 periodic y images: perBCx / perBCy,
         // boundary.h:38-46) and element offsets inside one padded field / one unpadded register array
-        const int tu = tid_now() & 31;
-        const int i = i0 + tu, j = j0 + ty;
+        const int tl = tid_now();
+        const int tu = tl & 31, tw = tl >> 5;
+        const int i = i0 + tu, j = j0 + tw;
         const unsigned flags = ((i < L.mx && j < L.my) ? 1u : 0u) | ((i < S) ? 2u : 0u) | ((i >= L.mx - S) ? 4u : 0u) |
                                ((j < S) ? 8u : 0u) | ((j >= L.my - S) ? 16u : 0u);
         const size_t gq = L.idx(i, j, k), nq = (size_t)i + (size_t)j * L.mx + (size_t)k * L.mx * L.my;
-        const int tl = ty * TX + tu;
         if (!do_update) {
             if (flags & 1u) {
 #pragma unroll
@@ -350,7 +435,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             // Runge-Kutta register update (sumLowStorageRK3 cuda_main.cu:244): Q_out = Q + dt (cN K + cA RA), RW = wNew K
             if (P.RW && (flags & 1u)) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) P.RW[m * N + nq] = sc.wNew * rhs[m];
+                for (int m = 0; m < 5; m++) st_out(P.RW + m * N + nq, sc.wNew * rhs[m]);
             }
             double kq[5];
 #pragma unroll
@@ -374,15 +459,15 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             if (flags & 1u) {
                 auto store_point = [&](double *f) {
 #pragma unroll
-                    for (int m = 0; m < 7; m++) f[m * L.vol] = out[m];
+                    for (int m = 0; m < 7; m++) st_out(f + m * L.vol, out[m]);
                     if (flags & 30u) {
 #pragma unroll
                         for (int m = 0; m < 7; m++) {
                             double *fm = f + m * L.vol;
-                            if (flags & 2u) fm[L.mx] = out[m];
-                            if (flags & 4u) fm[-(ptrdiff_t)L.mx] = out[m];
-                            if (flags & 8u) fm[(size_t)L.my * L.px] = out[m];
-                            if (flags & 16u) fm[-(ptrdiff_t)((size_t)L.my * L.px)] = out[m];
+                            if (flags & 2u) st_out(fm + L.mx, out[m]);
+                            if (flags & 4u) st_out(fm - (ptrdiff_t)L.mx, out[m]);
+                            if (flags & 8u) st_out(fm + (size_t)L.my * L.px, out[m]);
+                            if (flags & 16u) st_out(fm - (ptrdiff_t)((size_t)L.my * L.px), out[m]);
                         }
                     }
                 };
@@ -396,7 +481,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (ty == 0) tmem_dealloc(tmem0, G::NCOLS);
+    if ((tid_now() >> 5) == 0) tmem_dealloc(lds_u32_now(smem_u32(tmem_holder)), G::NCOLS);
 }
 
 // H, T of every cell of a padded 8-field state buffer (ghosts included) from its (rho,u,v,w,rho*E): for buffers this kernel did not write
@@ -414,7 +499,12 @@ template <int S, int V, int TY>
 static void launch_t(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, cudaStream_t st) {
     using G = FCfg<S, TY>;
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(stage_kernel<S, V, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(stage_kernel<S, V, TY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
+        cudaFuncSetAttribute(stage_kernel<S, V, TY, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
+        cudaFuncSetAttribute(stage_kernel<S, V, TY, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
+        attr_set = true;
+    }
     const int gx = (kc.L.mx + TX - 1) / TX, gy = (kc.L.my + TY - 1) / TY;
     // z chunks: every chunk pays a 2S-plane prologue, so keep them >= 32 planes; more chunks smooth the tail over the SMs
     const int cols = gx * gy, resident = 148 * (TY == 16 ? 1 : 2);
@@ -423,7 +513,9 @@ static void launch_t(const KConst &kc, const StagePtrs &p, const StageCoef &c, c
     int zchunk = (kc.L.mz + nzc - 1) / nzc;
     nzc = (kc.L.mz + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);
-    stage_kernel<S, V, TY><<<grid, TX * TY, G::bytes, st>>>(kc, p, c, zchunk, maps);
+    if (p.rhs_out) stage_kernel<S, V, TY, 0><<<grid, TX * TY, G::bytes, st>>>(kc, p, c, zchunk, maps);
+    else if (!p.RA) stage_kernel<S, V, TY, 1><<<grid, TX * TY, G::bytes, st>>>(kc, p, c, zchunk, maps);
+    else stage_kernel<S, V, TY, 2><<<grid, TX * TY, G::bytes, st>>>(kc, p, c, zchunk, maps);
 }
 template <int TY>
 static void launch_ty(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, cudaStream_t st) {

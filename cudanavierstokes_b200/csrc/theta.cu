@@ -6,10 +6,12 @@
 // writes theta once (32 B per point of HBM traffic, against 168 B of the stage kernel).
 //
 // Mapping: one CTA = a 32 x 16 tile of (i,j) columns marching along z, one thread per column.
-//   * du/dx and dv/dy read their neighbours from a double-buffered shared plane (u with x halos, v with y halos,
-//     one __syncthreads per plane); the loads of plane k+1 are issued before plane k is computed;
-//   * dw/dz keeps the 2V+1 most recent w values of the column in REGISTERS (a shifting window: 2V moves per plane,
-//     noise next to the memory time of this kernel);
+//   * the planes of u (with x halos), v (with y halos) and w travel global -> shared memory with cp.async (no register
+//     staging) through a ring of NST = 4 stages, three planes ahead of the one being computed: ~45 KB per CTA in flight,
+//     which is what 6.5 TB/s at ~1 us latency needs (the first version staged one plane ahead through registers and
+//     stopped at 56 % of the copy bandwidth); one __syncthreads per plane;
+//   * du/dx and dv/dy read their neighbours from the shared plane; dw/dz keeps the 2V+1 most recent w values of the column
+//     in REGISTERS (a shifting window: 2V moves per plane, noise next to the memory time of this kernel);
 //   * wall / extrapolation ghosts in x are built in shared memory (BCxderVel, boundary_condition_x.h:38-40,67,94),
 //     the z extrapolation of the boundary layer (BCzderVel, boundary_condition_z.h:34-40) is applied on the few
 //     planes next to the global z boundaries by a slow path that reads global memory directly.
@@ -20,6 +22,13 @@ namespace {
 
 constexpr int TXT = 32, TYT = 16, NTT = TXT * TYT;
 constexpr int UX = TXT + 2 * GX;
+constexpr int NST = 4;                                   // cp.async ring depth (planes)
+
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // wall blowing/suction, perturbation.h:25-53
 __device__ __forceinline__ bool perturb_theta(const KConst &c, int j, int kglob, double &val) {
@@ -60,9 +69,11 @@ template <int V, bool GEN>
 __global__ void __launch_bounds__(NTT, 2)
 theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ q, double *__restrict__ theta, int zchunk) {
     constexpr int VY = TYT + 2 * V;
-    constexpr int SU = TYT * UX, SV = VY * TXT;           // doubles per buffer
-    __shared__ double su[2 * SU];                         // [2][TYT][UX]
-    __shared__ double sv[2 * SV];                         // [2][VY][TXT]
+    constexpr int SU = TYT * UX, SV = VY * TXT, SW = NTT;  // doubles per stage
+    extern __shared__ __align__(16) double sth[];
+    double *su = sth;                                     // [NST][TYT][UX]
+    double *sv = su + NST * SU;                           // [NST][VY][TXT]
+    double *sw = sv + NST * SV;                           // [NST][TYT][TXT]
 
     const Layout &L = c.L;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -100,26 +111,31 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
     double wr[2 * V + 1];                                 // wr[V + l] = w of plane k+l
 #pragma unroll
     for (int m = 0; m < 2 * V; m++) wr[m + 1] = pw[(ptrdiff_t)(m - 2 * V) * (ptrdiff_t)plane];
-    // staged values of the next plane
-    double un = *pu, vn = *pv, wn = *pw, uhn = 0.0, vhn = 0.0;
-    if (hx_load) uhn = *puh;
-    if (hy_on) vhn = *pvh;
+    // plane kk (u, v at kk; w at kk+V) -> ring stage st; every thread commits exactly one group per call
+    const int o_w = ty * TXT + tx;
+    auto stage_plane = [&](int st) {
+        if (active) { cp_async8(su + st * SU + o_u, pu); cp_async8(sv + st * SV + o_v, pv); }   // (slots past a ragged tile edge belong to halo cells)
+        cp_async8(sw + st * SW + o_w, pw);
+        if (hx_load) cp_async8(su + st * SU + o_uh, puh);
+        if (hy_on) cp_async8(sv + st * SV + o_vh, pvh);
+        pu += plane; pv += plane; pw += plane; puh += plane; pvh += plane;
+    };
+#pragma unroll
+    for (int n = 0; n < NST - 1; n++) {
+        if (kfirst + n < klast) stage_plane(n);
+        cp_async_commit();
+    }
 
-    int boff_u = 0, boff_v = 0;
-    for (int k = kfirst; k < klast; k++) {
+    int st = 0;
+    for (int k = kfirst; k < klast; k++, st = (st + 1 == NST) ? 0 : st + 1) {
+        cp_async_wait<NST - 2>();                         // this thread's copies of plane k have landed ...
+        __syncthreads();                                  // ... and everybody else's; plane k-1 is consumed
+        if (k + NST - 1 < klast) stage_plane(st == 0 ? NST - 1 : st - 1);
+        cp_async_commit();
+        const int boff_u = st * SU, boff_v = st * SV;
 #pragma unroll
         for (int m = 0; m < 2 * V; m++) wr[m] = wr[m + 1];
-        wr[2 * V] = wn;
-        if (active) { su[boff_u + o_u] = un; sv[boff_v + o_v] = vn; }
-        if (hx_load) su[boff_u + o_uh] = uhn;
-        if (hy_on) sv[boff_v + o_vh] = vhn;
-        __syncthreads();
-        pu += plane; pv += plane; pw += plane; puh += plane; pvh += plane;
-        if (k + 1 < klast) {                             // stage plane k+1 (consumed at the top of the next iteration)
-            un = *pu; vn = *pv; wn = *pw;
-            if (hx_load) uhn = *puh;
-            if (hy_on) vhn = *pvh;
-        }
+        wr[2 * V] = sw[st * SW + o_w];
         const bool outside = bl && (k < kglob_lo || k >= kglob_hi);    // ghost theta is extrapolated by the stage kernel
         if constexpr (GEN) {
             if (xlo || xhi) {
@@ -166,7 +182,6 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
             }
         }
         pt += plane;
-        boff_u ^= SU; boff_v ^= SV;
     }
 }
 
@@ -183,14 +198,22 @@ void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaSt
     dim3 grid(gx, gy, nzc);
     const bool gen = !(kc.periodicX && !kc.nonUniformX && !kc.boundaryLayer);
 #define CUDNS_THETA_CASE(VV)                                                                        \
-    case VV:                                                                                        \
-        if (gen) theta_march_kernel<VV, true><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);          \
-        else theta_march_kernel<VV, false><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);             \
-        break;
+    {                                                                                               \
+        const size_t sm = (size_t)NST * (TYT * UX + (TYT + 2 * VV) * TXT + NTT) * sizeof(double);   \
+        static bool attr = false;                                                                   \
+        if (!attr) {                                                                                \
+            cudaFuncSetAttribute(theta_march_kernel<VV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
+            cudaFuncSetAttribute(theta_march_kernel<VV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
+            attr = true;                                                                            \
+        }                                                                                           \
+        if (gen) theta_march_kernel<VV, true><<<grid, NTT, sm, st>>>(kc, q, theta, zchunk);         \
+        else theta_march_kernel<VV, false><<<grid, NTT, sm, st>>>(kc, q, theta, zchunk);            \
+    }
     switch (kc.v) {
-        CUDNS_THETA_CASE(1) CUDNS_THETA_CASE(2) CUDNS_THETA_CASE(3)
-        default: if (gen) theta_march_kernel<4, true><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);
-                 else theta_march_kernel<4, false><<<grid, NTT, 0, st>>>(kc, q, theta, zchunk);
+        case 1: CUDNS_THETA_CASE(1) break;
+        case 2: CUDNS_THETA_CASE(2) break;
+        case 3: CUDNS_THETA_CASE(3) break;
+        default: CUDNS_THETA_CASE(4) break;
     }
 #undef CUDNS_THETA_CASE
 }
