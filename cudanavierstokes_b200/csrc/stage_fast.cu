@@ -119,6 +119,16 @@ __device__ __forceinline__ void slot_wait2(Slot &s, Slot &t, double (&q)[NF], do
                  :: "memory");
     slot_unpack(s, q); slot_unpack(t, w);
 }
+// ring slot store without the wait (tmem_st7d of stage_lean.inc waits at once): the slot is read back only by the last z step of
+// the plane, tmem_wait_st() goes in front of that load
+__device__ __forceinline__ void tmem_st7d_nowait(uint32_t ta, double a, double b, double c, double d, double e, double f, double g) {
+    asm volatile("{\n\t.reg .b32 x<14>;\n\tmov.b64 {x0,x1}, %1;\n\tmov.b64 {x2,x3}, %2;\n\tmov.b64 {x4,x5}, %3;\n\tmov.b64 {x6,x7}, %4;\n\t"
+                 "mov.b64 {x8,x9}, %5;\n\tmov.b64 {x10,x11}, %6;\n\tmov.b64 {x12,x13}, %7;\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {x0,x1,x2,x3,x4,x5,x6,x7};\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x4.b32 [%8], {x8,x9,x10,x11};\n\t"
+                 "tcgen05.st.sync.aligned.32x32b.x2.b32 [%9], {x12,x13};\n\t}"
+                 ::"r"(ta), "d"(a), "d"(b), "d"(c), "d"(d), "d"(e), "d"(f), "d"(g), "r"(ta + 8), "r"(ta + 12) : "memory");
+}
 // one double parked in / fetched from two tensor-memory columns
 __device__ __forceinline__ void tmem_st1d(uint32_t ta, double a) {
     asm volatile("{\n\t.reg .b32 x<2>;\n\tmov.b64 {x0,x1}, %1;\n\ttcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {x0,x1};\n\t}" ::"r"(ta), "d"(a) : "memory");
@@ -317,10 +327,11 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         slot_issue(zs[S], sl);
         {
             const double *src = intb + ty * TX + tx;
-            tmem_st7d(zs[2 * S], src[0], src[NT], src[2 * NT], src[3 * NT], src[4 * NT], src[5 * NT], src[6 * NT]);
+            const double r0 = src[0], r1 = src[NT], r2 = src[2 * NT], r3 = src[3 * NT], r4 = src[4 * NT], r5 = src[5 * NT], r6 = src[6 * NT];
+            __syncwarp();
+            if (tx == 0) mbar_arrive(mb_free);                    // intb is consumed as soon as the values sit in registers
+            tmem_st7d_nowait(zs[2 * S], r0, r1, r2, r3, r4, r5, r6);
         }
-        __syncwarp();
-        if (tx == 0) mbar_arrive(mb_free);
         double C[NF];
         slot_wait(sl, C);
 
@@ -337,10 +348,12 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
 #pragma unroll
             for (int l = 1; l <= S; l++) {
 #if FAST_ONESIDED
+                if (l == S) tmem_wait_st();
                 { Slot sp; slot_issue(zs[S + l], sp); double Nq[NF]; slot_wait(sp, Nq); side_step<2, V, true>(c, l, C, Nq, A, aM); }
                 { Slot sm; slot_issue(zs[S - l], sm); double Nq[NF]; slot_wait(sm, Nq); side_step<2, V, false>(c, l, C, Nq, A, aM); }
 #else
                 Slot sp, sm;
+                if (l == S) tmem_wait_st();                       // the slot of plane k+S was stored at the top of this plane
                 slot_issue(zs[S + l], sp); slot_issue(zs[S - l], sm);
                 double Pn[NF], Mn[NF];
                 slot_wait2(sp, sm, Pn, Mn);
@@ -425,17 +438,19 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         const int i = i0 + tu, j = j0 + tw;
         const unsigned flags = ((i < L.mx && j < L.my) ? 1u : 0u) | ((i < S) ? 2u : 0u) | ((i >= L.mx - S) ? 4u : 0u) |
                                ((j < S) ? 8u : 0u) | ((j >= L.my - S) ? 16u : 0u);
-        const size_t gq = L.idx(i, j, k), nq = (size_t)i + (size_t)j * L.mx + (size_t)k * L.mx * L.my;
+        // element offsets: a warp-uniform 64-bit part (tile origin, plane) and a 32-bit per-thread part
+        const size_t gq0 = L.idx(i0, j0, k), nq0 = (size_t)i0 + (size_t)j0 * L.mx + (size_t)k * L.mx * L.my;
+        const uint32_t gqt = (uint32_t)(tw * L.px + tu), nqt = (uint32_t)(tw * L.mx + tu);
         if (!do_update) {
             if (flags & 1u) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) P.rhs_out[m * N + nq] = rhs[m];
+                for (int m = 0; m < 5; m++) (P.rhs_out + m * N + nq0)[nqt] = rhs[m];
             }
         } else {
             // Runge-Kutta register update (sumLowStorageRK3 cuda_main.cu:244): Q_out = Q + dt (cN K + cA RA), RW = wNew K
             if (P.RW && (flags & 1u)) {
 #pragma unroll
-                for (int m = 0; m < 5; m++) st_out(P.RW + m * N + nq, sc.wNew * rhs[m]);
+                for (int m = 0; m < 5; m++) st_out((P.RW + m * N + nq0) + nqt, sc.wNew * rhs[m]);
             }
             double kq[5];
 #pragma unroll
@@ -457,13 +472,13 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             double out[7] = {qn[0], qn[1] * rn, qn[2] * rn, qn[3] * rn, qn[4], 0.0, 0.0};
             eos_ht(c, out[0], rn, out[1], out[2], out[3], out[4], out[5], out[6]);          // H and T travel with the state
             if (flags & 1u) {
-                auto store_point = [&](double *f) {
+                auto store_point = [&](double *fu) {                // fu: warp-uniform (tile origin of the plane)
 #pragma unroll
-                    for (int m = 0; m < 7; m++) st_out(f + m * L.vol, out[m]);
+                    for (int m = 0; m < 7; m++) st_out((fu + m * L.vol) + gqt, out[m]);
                     if (flags & 30u) {
 #pragma unroll
                         for (int m = 0; m < 7; m++) {
-                            double *fm = f + m * L.vol;
+                            double *fm = (fu + m * L.vol) + gqt;
                             if (flags & 2u) st_out(fm + L.mx, out[m]);
                             if (flags & 4u) st_out(fm - (ptrdiff_t)L.mx, out[m]);
                             if (flags & 8u) st_out(fm + (size_t)L.my * L.px, out[m]);
@@ -471,11 +486,11 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
                         }
                     }
                 };
-                store_point(P.qout + gq);
+                store_point(P.qout + gq0);
                 // z ghosts (replaces updateHaloFive comm.cpp:114-134 / perBCz boundary.h:48-51): the first / last gz planes also go
                 // into the ghost planes of the lower / upper slab neighbour -- peer memory over NVLink, or this buffer itself
-                if (k < L.gz && P.qout_lo) store_point(P.qout_lo + gq + (size_t)L.mz * L.plane);
-                if (k >= L.mz - L.gz && P.qout_hi) store_point(P.qout_hi + gq - (size_t)L.mz * L.plane);
+                if (k < L.gz && P.qout_lo) store_point(P.qout_lo + gq0 + (size_t)L.mz * L.plane);
+                if (k >= L.mz - L.gz && P.qout_hi) store_point(P.qout_hi + gq0 - (size_t)L.mz * L.plane);
             }
         }
     }

@@ -1,0 +1,10 @@
+#!/bin/bash
+# short multi-GPU session (run under gpurun --gpus N): multi == single parity for both transports, one bench line
+N=${1:-2}; TAG=${2:-m}; mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+{
+timeout 300 $TR tools/mgpu_check.py 64 5 peer tgv 2>&1 | grep -E "mgpu_check|Error|error"
+timeout 300 $TR tools/mgpu_check.py 64 5 nccl tgv 2>&1 | grep -E "mgpu_check|Error|error"
+timeout 300 $TR tools/mgpu_check.py 64 4 peer kutta 2>&1 | grep -E "mgpu_check|Error|error"
+timeout 600 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1
+} 2>&1 | tee gpurun_out/${TAG}_mgpu${N}.log
