@@ -119,6 +119,45 @@ def test_narrow_tile_variant_of_the_stage_kernel(sv, monkeypatch):
     assert max(errs) < TOL, errs
 
 
+@pytest.mark.parametrize("shape", [(40, 20, 24), (24, 36, 16), (70, 10, 12), (32, 8, 72)])
+def test_fast_kernel_ragged_tiles_and_z_chunks(shape):
+    """linear viscosity + periodic box = the fourth-generation stage kernel (8-field state buffers, H and T written with the
+    state): grids that are not multiples of its 32 x 8 tile, a tall one that is split into z chunks, smooth random field;
+    right-hand side and 7 steps (first stage from derive_aux_kernel, the others from the H,T the kernel itself stored)"""
+    op = ob.params_tgv(24, 4, mx=shape[0], my=shape[1], mz=shape[2], Lx=3.0, Ly=5.0, Lz=4.0)
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    _rhs_check(o, s)
+    o.run(7); s.advance(7)
+    errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+    assert max(errs) < TOL, errs
+
+
+def _advance_with_env(monkeypatch, env, nsteps, sv=(4, 4)):
+    for k in ("CUDNS_WIDE", "CUDNS_FAST_TY"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    op = ob.params_tgv(32, sv[0], stencilVisc=sv[1], mz=48)
+    o, s, grid = make_pair(op)
+    o.init_chit(); s.set_state(o.state())
+    s.advance(nsteps)
+    return conserved(s.get_state())
+
+
+def test_stage_kernel_generations_agree(monkeypatch):
+    """the same 12 Taylor-Green steps through the fast kernel with its 8-warp and its 16-warp tile (identical arithmetic per
+    point: bit for bit), and through the lean wide / lean kernels (p staged instead of rebuilt from rho*T: round-off)"""
+    a8 = _advance_with_env(monkeypatch, {}, 12)
+    a16 = _advance_with_env(monkeypatch, {"CUDNS_FAST_TY": "16"}, 12)
+    for x, y in zip(a8, a16):
+        assert np.array_equal(x, y)
+    for env in ({"CUDNS_WIDE": "1"}, {"CUDNS_WIDE": "0"}):
+        b = _advance_with_env(monkeypatch, env, 12)
+        errs = [relerr(x, y) for x, y in zip(a8, b)]
+        assert max(errs) < 1e-13, (env, errs)
+
+
 def test_dt_and_bulk():
     op = ob.params_tgv(24, 3)
     o, s, grid = make_pair(op)
