@@ -232,6 +232,7 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    c1 = sol.counters()
     # nvidia-smi delivers a sample every ~100 ms: when the timed region was shorter than that (many GPUs, small K), the same
     # workload keeps running untimed until the sampler has seen it for ~0.8 s, so the clocks line describes this load
     extra = 0
@@ -242,7 +243,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["covers"] = "timed region" if extra == 0 else "timed region + %d untimed steps of the same workload" % extra
-    c1 = sol.counters()
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -155,7 +155,8 @@ def test_stage_kernel_generations_agree(monkeypatch):
     for env in ({"CUDNS_WIDE": "1"}, {"CUDNS_WIDE": "0"}):
         b = _advance_with_env(monkeypatch, env, 12)
         errs = [relerr(x, y) for x, y in zip(a8, b)]
-        assert max(errs) < 1e-13, (env, errs)
+        # rho*w of the Taylor-Green start is a small (1e-2-sized) response, so round-off relative to ITS max is the largest
+        assert max(errs) < TOL, (env, errs)
 
 
 def test_dt_and_bulk():
