@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDNS_LIB", os.path.join(_HERE, "libcudns.so"))   # o
 CSRC = os.path.join(_HERE, "csrc")
 
 __all__ = ["Params", "PeerInfo", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",
-           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "EXPORTS"]
+           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "write_xdmf", "EXPORTS"]
 
 # every symbol include/cudns.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -30,6 +30,7 @@ EXPORTS = [
     "cudns_calc_rhs", "cudns_calc_dt", "cudns_calc_bulk", "cudns_get_scalars", "cudns_set_dt",
     "cudns_halo_local_info", "cudns_halo_connect", "cudns_halo_buffers", "cudns_set_allreduce",
     "cudns_set_exchange", "cudns_get_stream", "cudns_get_counters", "cudns_profile_stage",
+    "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
 ]
 
 
@@ -131,6 +132,10 @@ def lib():
     L.cudns_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     L.cudns_get_counters.argtypes = [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.cudns_profile_stage.argtypes = [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cudns_write_fields_async.argtypes = [H, C.c_char_p, C.c_int]
+    L.cudns_io_wait.argtypes = [H, C.POINTER(C.c_uint64)]
+    L.cudns_read_fields.argtypes = [H, C.c_char_p, C.c_int]
+    L.cudns_write_xdmf.argtypes = [C.c_char_p, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_char_p]
     _lib = L
     return L
 
@@ -209,6 +214,14 @@ def read_field(directory, name, timestep, shape):
     a = np.zeros(shape)
     _check(lib().cudns_read_field(directory.encode(), name.encode(), timestep, _dp(a), a.size))
     return a
+
+
+def write_xdmf(path, x, y, z, timesteps, dt, names="ruvwe", single_precision=False):
+    """XDMF sidecar for the fields/ directory (python-utils/writexmf.py)"""
+    x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64); z = np.ascontiguousarray(z, dtype=np.float64)
+    ts = (C.c_int * len(timesteps))(*[int(t) for t in timesteps])
+    _check(lib().cudns_write_xdmf(str(path).encode(), int(single_precision), _dp(x), x.size, _dp(y), y.size, _dp(z), z.size,
+                                  ts, len(timesteps), float(dt), names.encode()))
 
 
 class Solver:
@@ -314,6 +327,19 @@ class Solver:
 
     def stream(self):
         s = C.c_void_p(); _check(self.L.cudns_get_stream(self.h, C.byref(s))); return s.value
+
+    def write_fields_async(self, directory, timestep):
+        """snapshot the current state into fields/{r,u,v,w,e}.<timestep>.bin without stalling the step loop"""
+        _check(lib().cudns_write_fields_async(self.h, str(directory).encode(), int(timestep)))
+
+    def io_wait(self):
+        n = C.c_uint64(0)
+        _check(lib().cudns_io_wait(self.h, C.byref(n)))
+        return int(n.value)
+
+    def read_fields(self, directory, timestep):
+        """restart from fields/{r,u,v,w,e}.<timestep>.bin"""
+        _check(lib().cudns_read_fields(self.h, str(directory).encode(), int(timestep)))
 
     def profile_stage(self, reps=3):
         a = C.c_float(0); b = C.c_float(0); c = C.c_float(0)

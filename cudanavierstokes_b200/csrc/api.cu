@@ -6,6 +6,11 @@
 #include <cstring>
 #include <cstdlib>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 namespace cudns {
 const double *coeff_first(int s);
@@ -27,7 +32,23 @@ using namespace cudns;
 // device scalar slots
 enum { SC_DT = 0, SC_DPDZ, SC_TGPU, SC_TIME, SC_RED0, SC_RED1, SC_STALE0, SC_STALE1, SC_BULK0, SC_BULK1, SC_BULK2, SC_BULK3, SC_N = 16 };
 
+// asynchronous fields/ writer: one snapshot in flight
+struct IoState {
+    cudaStream_t cs = nullptr;          // copy stream
+    double *d_stage = nullptr;          // compact copy of the slab on the device [5][mz][my][mx]
+    double *h_stage = nullptr;          // the same in pinned host memory
+    cudaEvent_t snap_done = nullptr, d2h_done = nullptr;
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable cv;
+    bool started = false, stop = false, busy = false, have_job = false;
+    std::string dir; int timestep = 0;
+    int err = 0; std::string errmsg;
+    uint64_t files_written = 0;
+};
+
 struct cudns_solver {
+    IoState *io;
     cudns_params P;
     KConst kc;
     Layout L;
@@ -284,9 +305,12 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     return CUDNS_OK;
 }
 
+static void io_shutdown(cudns_solver *S);
+
 int cudns_destroy(cudns_handle S) {
     if (!S) return CUDNS_OK;
     cudaSetDevice(S->P.device);
+    io_shutdown(S);
     if (S->st) cudaStreamSynchronize(S->st);
     if (S->ipc_lo) cudaIpcCloseMemHandle(S->ipc_lo);
     if (S->ipc_hi && S->ipc_hi != S->ipc_lo) cudaIpcCloseMemHandle(S->ipc_hi);
@@ -758,6 +782,149 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
     if (ms_theta) *ms_theta = t_th / reps; if (ms_rhs) *ms_rhs = t_rhs / reps; if (ms_halo) *ms_halo = t_h / reps;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     return CUDNS_OK;
+}
+
+}  // extern "C"
+
+
+// ---- asynchronous output and restart (writeField / initField, init.cpp:13-30; saveFileMPI / readFileMPI, comm.cpp:205-279) --------
+// fields/<c>.<%07d>.bin holds the GLOBAL field [mz_tot][my][mx], raw float64, no header; with z slabs a rank's share is one
+// contiguous byte range, so every rank pwrite()s its slab at its offset (what the reference does with an MPI-IO subarray view).
+// The step loop is never stalled: the snapshot is a device-side copy on the solver's stream (unpad kernel, ~2 ms at 512^3), the
+// D2H copy runs on a second stream into pinned memory, the file system is driven by a writer thread.
+static void io_worker(cudns_solver *S) {
+    IoState *io = S->io;
+    cudaSetDevice(S->P.device);
+    for (;;) {
+        std::string dir; int ts;
+        {
+            std::unique_lock<std::mutex> lk(io->m);
+            io->cv.wait(lk, [&] { return io->have_job || io->stop; });
+            if (!io->have_job && io->stop) return;
+            dir = io->dir; ts = io->timestep; io->have_job = false;
+        }
+        int err = 0; std::string msg;
+        cudaError_t ce = cudaEventSynchronize(io->d2h_done);
+        if (ce != cudaSuccess) { err = CUDNS_ECUDA; msg = std::string("fields writer: ") + cudaGetErrorString(ce); }
+        const size_t N = S->N;
+        const off_t off = (off_t)S->P.rank * (off_t)N * (off_t)sizeof(double);
+        const char names[5] = {'r', 'u', 'v', 'w', 'e'};
+        for (int f = 0; f < 5 && !err; f++) {
+            char path[1200];
+            std::snprintf(path, sizeof(path), "%s/fields/%c.%07d.bin", dir.c_str(), names[f], ts);
+            int fd = ::open(path, O_CREAT | O_WRONLY, 0644);
+            if (fd < 0) { err = CUDNS_EINVAL; msg = std::string("cannot open ") + path; break; }
+            const char *src = (const char *)(io->h_stage + (size_t)f * N);
+            size_t left = N * sizeof(double); off_t o = off;
+            while (left > 0) {
+                ssize_t w = ::pwrite(fd, src, left > ((size_t)1 << 30) ? ((size_t)1 << 30) : left, o);
+                if (w <= 0) { err = CUDNS_EINVAL; msg = std::string("short write ") + path; break; }
+                src += w; o += w; left -= (size_t)w;
+            }
+            ::close(fd);
+            if (!err) io->files_written++;
+        }
+        {
+            std::lock_guard<std::mutex> lk(io->m);
+            if (err && !io->err) { io->err = err; io->errmsg = msg; }
+            io->busy = false;
+        }
+        io->cv.notify_all();
+    }
+}
+
+static int io_start(cudns_solver *S) {
+    if (S->io && S->io->started) return CUDNS_OK;
+    if (!S->io) S->io = new IoState();
+    IoState *io = S->io;
+    const size_t bytes = 5 * S->N * sizeof(double);
+    CK(cudaStreamCreateWithFlags(&io->cs, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **)&io->d_stage, bytes));
+    CK(cudaMallocHost((void **)&io->h_stage, bytes));
+    CK(cudaEventCreateWithFlags(&io->snap_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&io->d2h_done, cudaEventDisableTiming));
+    S->bytes += bytes;
+    io->worker = std::thread(io_worker, S);
+    io->started = true;
+    return CUDNS_OK;
+}
+
+static void io_shutdown(cudns_solver *S) {
+    IoState *io = S->io;
+    if (!io) return;
+    if (io->started) {
+        { std::lock_guard<std::mutex> lk(io->m); io->stop = true; }
+        io->cv.notify_all();
+        if (io->worker.joinable()) io->worker.join();
+    }
+    if (io->cs) cudaStreamDestroy(io->cs);
+    cudaFree(io->d_stage); cudaFreeHost(io->h_stage);
+    if (io->snap_done) cudaEventDestroy(io->snap_done);
+    if (io->d2h_done) cudaEventDestroy(io->d2h_done);
+    delete io; S->io = nullptr;
+}
+
+extern "C" {
+
+int cudns_write_fields_async(cudns_handle S, const char *dir, int timestep) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    int rc = io_start(S); if (rc) return rc;
+    IoState *io = S->io;
+    {   // one snapshot in flight: the staging buffers are free once the previous one is on disk
+        std::unique_lock<std::mutex> lk(io->m);
+        io->cv.wait(lk, [&] { return !io->busy; });
+        if (io->err) { set_error(io->errmsg); return io->err; }
+    }
+    std::string d = dir ? dir : ".";
+    ::mkdir(d.c_str(), 0755);
+    ::mkdir((d + "/fields").c_str(), 0755);
+    const size_t N = S->N;
+    double *dst[5] = {io->d_stage, io->d_stage + N, io->d_stage + 2 * N, io->d_stage + 3 * N, io->d_stage + 4 * N};
+    launch_unpad(S->kc, S->state[S->cur], dst, S->st); S->launches++;
+    CK(cudaEventRecord(io->snap_done, S->st));
+    CK(cudaStreamWaitEvent(io->cs, io->snap_done, 0));
+    CK(cudaMemcpyAsync(io->h_stage, io->d_stage, 5 * N * sizeof(double), cudaMemcpyDeviceToHost, io->cs));
+    CK(cudaEventRecord(io->d2h_done, io->cs));
+    {
+        std::lock_guard<std::mutex> lk(io->m);
+        io->dir = d; io->timestep = timestep; io->have_job = true; io->busy = true;
+    }
+    io->cv.notify_all();
+    return CUDNS_OK;
+}
+
+int cudns_io_wait(cudns_handle S, uint64_t *files_written) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    IoState *io = S->io;
+    if (files_written) *files_written = 0;
+    if (!io || !io->started) return CUDNS_OK;
+    std::unique_lock<std::mutex> lk(io->m);
+    io->cv.wait(lk, [&] { return !io->busy; });
+    if (files_written) *files_written = io->files_written;
+    if (io->err) { set_error(io->errmsg); int e = io->err; io->err = 0; return e; }
+    return CUDNS_OK;
+}
+
+// restart: this rank's slab of fields/{r,u,v,w,e}.<timestep>.bin -> cudns_set_state (readFileMPI reads the whole file on rank 0
+// and broadcasts it; here every rank seeks to its own byte range)
+int cudns_read_fields(cudns_handle S, const char *dir, int timestep) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    const size_t N = S->N;
+    std::vector<double> buf(5 * N);
+    const char names[5] = {'r', 'u', 'v', 'w', 'e'};
+    for (int f = 0; f < 5; f++) {
+        char path[1200];
+        std::snprintf(path, sizeof(path), "%s/fields/%c.%07d.bin", dir ? dir : ".", names[f], timestep);
+        FILE *fp = std::fopen(path, "rb");
+        if (!fp) { set_error(std::string("cannot open ") + path); return CUDNS_EINVAL; }
+        if (fseeko(fp, (off_t)S->P.rank * (off_t)N * (off_t)sizeof(double), SEEK_SET) != 0) { std::fclose(fp); set_error(std::string("cannot seek ") + path); return CUDNS_EINVAL; }
+        size_t n = std::fread(buf.data() + (size_t)f * N, sizeof(double), N, fp);
+        std::fclose(fp);
+        if (n != N) { set_error(std::string("short read ") + path); return CUDNS_EINVAL; }
+    }
+    return cudns_set_state(S, buf.data(), buf.data() + N, buf.data() + 2 * N, buf.data() + 3 * N, buf.data() + 4 * N);
 }
 
 }  // extern "C"

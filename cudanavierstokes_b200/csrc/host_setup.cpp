@@ -274,4 +274,47 @@ int cudns_read_field(const char *dir, char name, int timestep, double *var, size
     return CUDNS_OK;
 }
 
+
+// XDMF 2.0 sidecar for the fields/ directory (what python-utils/writexmf.py + makexmf.py produce): a 3DRectMesh with the VXVYVZ
+// coordinates inline, one temporal collection, one uniform grid per saved time step whose attributes point at <name>.<%07d>.bin.
+// names: one character per field ("ruvwe"); time of step t = t * dt.
+int cudns_write_xdmf(const char *path, int single_precision, const double *x, int nx, const double *y, int ny, const double *z, int nz,
+                     const int *timesteps, int nt, double dt, const char *names) {
+    if (!path || !x || !y || !z || (!timesteps && nt > 0) || !names) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    FILE *f = std::fopen(path, "wt");
+    if (!f) { set_error(std::string("cannot open ") + path); return CUDNS_EINVAL; }
+    const int prec = single_precision ? 4 : 8;
+    auto axis = [&](const char *indent, const double *v, int n) {
+        std::fprintf(f, "%s<DataItem Format=\"XML\" DataType=\"Float\" Precision=\"%d\" Dimensions=\"%5d\">\n", indent, prec, n);
+        for (int i = 0; i < n; i++) std::fprintf(f, "%15.6E", v[i]);
+        std::fprintf(f, "\n%s</DataItem>\n", indent);
+    };
+    std::fprintf(f, "<?xml version=\"1.0\" ?>\n<!DOCTYPE Xdmf SYSTEM \"Xdmf.dtd\" []>\n");
+    std::fprintf(f, "<Xdmf xmlns:xi=\"http://www.w3.org/2001/XInclude\" Version=\"2.0\">\n<Domain>\n");
+    std::fprintf(f, "    <Topology name=\"TOPO\" TopologyType=\"3DRectMesh\" Dimensions=\"%5d%5d%5d\"/>\n", nz, ny, nx);
+    std::fprintf(f, "    <Geometry name=\"GEO\" GeometryType=\"VXVYVZ\">\n");
+    axis("        ", x, nx); axis("        ", y, ny); axis("        ", z, nz);
+    std::fprintf(f, "    </Geometry>\n");
+    std::fprintf(f, "    <Grid Name=\"TimeSeries\" GridType=\"Collection\" CollectionType=\"Temporal\">\n        <Time TimeType=\"List\">\n");
+    {
+        std::vector<double> tv(nt);
+        for (int i = 0; i < nt; i++) tv[i] = timesteps[i] * dt;
+        axis("            ", tv.data(), nt);
+    }
+    std::fprintf(f, "        </Time>\n");
+    for (int i = 0; i < nt; i++) {
+        std::fprintf(f, "        <Grid Name=\"T%07d\" GridType=\"Uniform\">\n", timesteps[i]);
+        std::fprintf(f, "            <Topology Reference=\"/Xdmf/Domain/Topology[1]\"/>\n            <Geometry Reference=\"/Xdmf/Domain/Geometry[1]\"/>\n");
+        for (const char *c = names; *c; c++) {
+            std::fprintf(f, "            <Attribute Name=\"%c\" Center=\"Node\">\n", *c);
+            std::fprintf(f, "                <DataItem Format=\"Binary\" DataType=\"Float\" Precision=\"%d\" Endian=\"Native\" Dimensions=\"%5d%5d%5d\">\n", prec, nz, ny, nx);
+            std::fprintf(f, "                    %c.%07d.bin\n                </DataItem>\n            </Attribute>\n", *c, timesteps[i]);
+        }
+        std::fprintf(f, "        </Grid>\n");
+    }
+    std::fprintf(f, "    </Grid>\n</Domain>\n</Xdmf>\n");
+    if (std::fclose(f) != 0) { set_error(std::string("write error ") + path); return CUDNS_EINVAL; }
+    return CUDNS_OK;
+}
+
 }  // extern "C"

@@ -97,6 +97,10 @@ int cudns_build_sponge(const cudns_params *p, const double *x, const double *z,
  * [mz_tot][my_tot][mx_tot], no header.  dir is the directory that contains "fields". */
 int cudns_write_field(const char *dir, char name, int timestep, const double *var, size_t count);
 int cudns_read_field(const char *dir, char name, int timestep, double *var, size_t count);
+/* XDMF 2.0 sidecar describing fields/<c>.<%07d>.bin for ParaView/VisIt (python-utils/writexmf.py:1-77, makexmf.py): rectilinear
+ * mesh with inline coordinates, one temporal collection; names = one character per field ("ruvwe"), time of step t = t*dt. */
+int cudns_write_xdmf(const char *path, int single_precision, const double *x, int nx, const double *y, int ny, const double *z, int nz,
+                     const int *timesteps, int nt, double dt, const char *names);
 
 /* ---- solver life cycle ----------------------------------------------------------------- */
 /* setDevice + setGPUParameters + initSolver (cuda_utils.cu:815,49-179,415-519).  x,xp,xpp are the
@@ -175,6 +179,19 @@ int cudns_get_stream(cudns_handle h, void **stream);
 int cudns_get_counters(cudns_handle h, uint64_t *kernel_launches, uint64_t *rk_stages);
 /* per-kernel device time of the last cudns_profile_stage() call, in ms: theta, rhs_stage, halo */
 int cudns_profile_stage(cudns_handle h, int reps, float *ms_theta, float *ms_rhs, float *ms_halo);
+
+/* ---- output and restart that do not stall the step loop ------------------------------------------
+ * writeField (init.cpp:23-30) -> saveFileMPI (comm.cpp:205-250): fields/{r,u,v,w,e}.<%07d>.bin of the GLOBAL grid, raw float64
+ * [mz_tot][my][mx].  cudns_write_fields_async snapshots the current state on the device (stream-ordered with cudns_advance),
+ * returns at once, copies it to pinned host memory on a second stream and lets a writer thread pwrite() this rank's slab at its
+ * byte offset (the role of the reference's MPI-IO subarray view).  One snapshot is in flight per handle: the next call waits
+ * for the previous one to reach the disk.  dir is the directory that contains "fields" (created if missing). */
+int cudns_write_fields_async(cudns_handle h, const char *dir, int timestep);
+/* block until every snapshot is on disk; returns (and clears) the first writer error; files_written may be NULL */
+int cudns_io_wait(cudns_handle h, uint64_t *files_written);
+/* initField (init.cpp:13-21) -> readFileMPI (comm.cpp:252-279) + copyField(0): restart from fields/{r,u,v,w,e}.<%07d>.bin; every
+ * rank reads its own slab */
+int cudns_read_fields(cudns_handle h, const char *dir, int timestep);
 
 #ifdef __cplusplus
 }
