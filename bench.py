@@ -100,19 +100,25 @@ def scheme_params(cd, n, scheme):
 
 
 def tgv_slab(out, grid, p, k0, mzl):
+    """Taylor-Green initial condition of planes [k0, k0+mzl) (the formulas of initCHIT, init.cpp:126-148), a few planes at a
+    time so that the temporaries stay small next to the slab itself (1024^3 on 8 ranks: 5.4 GB of pinned state per rank)"""
     import numpy as np
     Rgas = float(np.float32(1.0) / np.float64(p.gam * p.Ma * p.Ma))
-    fx = 2 * np.pi * grid["x"] / p.Lx; fy = 2 * np.pi * grid["y"] / p.Ly; fz = 2 * np.pi * grid["z"][k0:k0 + mzl] / p.Lz
+    fx = 2 * np.pi * grid["x"] / p.Lx; fy = 2 * np.pi * grid["y"] / p.Ly
     sx, cx, c2x = np.sin(fx)[None, None, :], np.cos(fx)[None, None, :], np.cos(2 * fx)[None, None, :]
     sy, cy, c2y = np.sin(fy)[None, :, None], np.cos(fy)[None, :, None], np.cos(2 * fy)[None, :, None]
-    cz, c2z = np.cos(fz)[:, None, None], np.cos(2 * fz)[:, None, None]
+    uxy, vxy, pxy = sx * cy, -cx * sy, c2x + c2y
     r, u, v, w, e = out
-    u[...] = sx * cy * cz
-    v[...] = -cx * sy * cz
-    w[...] = 0.0
-    press = Rgas + (1.0 / 16.0) * (c2x + c2y) * (c2z + 2.0)
-    r[...] = press / Rgas
-    e[...] = press / (p.gam - 1.0) + 0.5 * r * (u * u + v * v)
+    for a in range(0, mzl, 8):
+        b = min(a + 8, mzl)
+        fz = 2 * np.pi * grid["z"][k0 + a:k0 + b] / p.Lz
+        cz, c2z = np.cos(fz)[:, None, None], np.cos(2 * fz)[:, None, None]
+        u[a:b] = uxy * cz
+        v[a:b] = vxy * cz
+        w[a:b] = 0.0
+        press = Rgas + (1.0 / 16.0) * pxy * (c2z + 2.0)
+        r[a:b] = press / Rgas
+        e[a:b] = press / (p.gam - 1.0) + 0.5 * r[a:b] * (u[a:b] * u[a:b] + v[a:b] * v[a:b])
 
 
 def cpu_oracle_rate(scheme, budget_s=12.0, n=128):

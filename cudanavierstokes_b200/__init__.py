@@ -31,6 +31,7 @@ EXPORTS = [
     "cudns_halo_local_info", "cudns_halo_connect", "cudns_halo_buffers", "cudns_set_allreduce",
     "cudns_set_exchange", "cudns_get_stream", "cudns_get_counters", "cudns_profile_stage",
     "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
+    "cudns_calc_profiles", "cudns_calc_retau",
 ]
 
 
@@ -133,6 +134,8 @@ def lib():
     L.cudns_get_counters.argtypes = [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.cudns_profile_stage.argtypes = [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cudns_write_fields_async.argtypes = [H, C.c_char_p, C.c_int]
+    L.cudns_calc_profiles.argtypes = [H, dp]
+    L.cudns_calc_retau.argtypes = [H, dp]
     L.cudns_io_wait.argtypes = [H, C.POINTER(C.c_uint64)]
     L.cudns_read_fields.argtypes = [H, C.c_char_p, C.c_int]
     L.cudns_write_xdmf.argtypes = [C.c_char_p, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_char_p]
@@ -327,6 +330,17 @@ class Solver:
 
     def stream(self):
         s = C.c_void_p(); _check(self.L.cudns_get_stream(self.h, C.byref(s))); return s.value
+
+    def profiles(self):
+        """y-z averaged wall-normal profiles (calcAvgChan): rows rho, u~, v~, w~, rho E, then their mean squares"""
+        out = np.zeros((10, self.p.mx))
+        _check(self.L.cudns_calc_profiles(self.h, _dp(out)))
+        return out
+
+    def retau(self):
+        v = C.c_double(0.0)
+        _check(self.L.cudns_calc_retau(self.h, C.byref(v)))
+        return v.value
 
     def write_fields_async(self, directory, timestep):
         """snapshot the current state into fields/{r,u,v,w,e}.<timestep>.bin without stalling the step loop"""

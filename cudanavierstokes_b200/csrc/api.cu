@@ -68,14 +68,14 @@ struct cudns_solver {
     double *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
     double *d_scal;
     double *d_hist; int hist_cap;
+    double *d_prof;              // profile diagnostics scratch: partial[64][5][mx], mean[5][mx], var[5][mx], 1 scalar (lazy)
     double *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
     bool have_state, fixed_dt, have_sponge;
     cudns_allreduce_fn allreduce; void *allreduce_user;
     cudns_exchange_fn exchange; void *exchange_user;
     uint64_t launches, stages;
     size_t bytes;
-    StageMaps maps[3];           // TMA descriptors of state[b] (+ theta), tile of the second-generation kernel
-    StageMaps lmaps[3];          // the same for the tile of the lean kernel
+    StageMaps lmaps[3];          // TMA descriptors of state[b] (+ theta), tile of the lean kernel
     CUtensorMap rmap[2];         // R1 / R2 (unpadded register arrays), tile interior of the lean kernel
     StageMaps wmaps[3];          // tile of the wide (16-warp) lean kernel
     CUtensorMap wrmap[2];
@@ -86,7 +86,6 @@ struct cudns_solver {
     FastMaps fmaps[3];           // its TMA descriptors per state buffer (opa is patched per launch)
     CUtensorMap frmap[2];        // R1 / R2 with its tile
     bool aux_valid[3];           // H, T of state[b] (ghosts included) match its (rho,u,v,w,rho*E)
-    int stage_gen;               // 3: lean kernel (default); CUDNS_STAGE=tmem -> 2, CUDNS_STAGE=smem -> 1 (A/B timing only)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcudns does not link libcuda)
@@ -252,21 +251,9 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
     CK(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
-    {
-        const char *env = getenv("CUDNS_STAGE");
-        S->stage_gen = !env ? 3 : std::string(env) == "smem" ? 1 : std::string(env) == "tmem" ? 2 : 3;
-    }
-    if ((size_t)stage_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin ||
-        (size_t)rhs_stage_smem_bytes(s) > prop.sharedMemPerBlockOptin ||
-        (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    if ((size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
-        const int ty = stage_tile_y(), CXb = 32 + 2 * GX, CYb = ty + 2 * s;
-        for (int b = 0; b < S->nstate; b++) {
-            if ((rc = make_map(&S->maps[b].qbox, L, S->state[b], 5, CXb, CYb)) || (rc = make_map(&S->maps[b].qint, L, S->state[b], 5, 32, ty)) ||
-                (rc = make_map(&S->maps[b].thbox, L, S->theta, 1, CXb, CYb)) || (rc = make_map(&S->maps[b].thint, L, S->theta, 1, 32, ty))) {
-                cudns_destroy(S); return rc;
-            }
-        }
+        const int CXb = 32 + 2 * GX;
         const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lty + 2 * s;
         for (int b = 0; b < S->nstate; b++) {
             if ((rc = make_map(&S->lmaps[b].qbox, L, S->state[b], 5, CXb, LYb)) || (rc = make_map(&S->lmaps[b].qint, L, S->state[b], 5, 32, lty)) ||
@@ -317,7 +304,7 @@ int cudns_destroy(cudns_handle S) {
     cudaFree(S->block);
     cudaFree(S->theta); cudaFree(S->R1); cudaFree(S->R2);
     cudaFree(S->d_xp); cudaFree(S->d_cVSx); cudaFree(S->d_dxv); cudaFree(S->d_spx); cudaFree(S->d_spz); cudaFree(S->d_sref);
-    cudaFree(S->d_scal); cudaFree(S->d_hist);
+    cudaFree(S->d_scal); cudaFree(S->d_hist); cudaFree(S->d_prof);
     cudaFree(S->send_lo); cudaFree(S->send_hi); cudaFree(S->recv_lo); cudaFree(S->recv_hi);
     if (S->st) cudaStreamDestroy(S->st);
     delete S;
@@ -510,10 +497,7 @@ int cudns_get_scalars(cudns_handle S, double *dt, double *dpdz, double *time) {
 
 // the stage kernel of the selected generation; p.qin = state[in], p.qbase = state[base]
 static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoef &c, int in, int base) {
-    const bool lean_ok = true;      // (no scheme of cudns_advance needs RB and the old RW in the same stage)
-    if (S->stage_gen == 1) launch_rhs_stage_smem(S->kc, p, c, S->st);
-    else if (S->stage_gen == 2 || !lean_ok) launch_rhs_stage(S->kc, p, c, S->maps[in], S->st);
-    else {
+    {
         // the wide variant stages one operand tile only (RA): every low-storage RK3 stage and the test path qualify
         const bool wide = S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
         if (wide && S->fast) {
@@ -539,12 +523,12 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
 
 // will launch_stage_any serve this stage with the fast kernel?
 static bool stage_is_fast(const cudns_solver *S, const StagePtrs &p, const StageCoef &c) {
-    return S->stage_gen == 3 && S->fast && S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
+    return S->fast && S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
 }
 
 // does this solver's stage kernel write the z ghost planes itself (lean kernel; on one device always, across devices once
 // the peer blocks are mapped)?
-static bool inkernel_ghosts(const cudns_solver *S) { return S->stage_gen == 3 && (S->P.nranks == 1 || S->connected); }
+static bool inkernel_ghosts(const cudns_solver *S) { return S->P.nranks == 1 || S->connected; }
 
 // neighbour-side addresses of output buffer `out` for the stage kernel (see StagePtrs::qout_lo / qout_hi)
 static void ghost_targets(cudns_solver *S, int out, StagePtrs &p) {
@@ -925,6 +909,55 @@ int cudns_read_fields(cudns_handle S, const char *dir, int timestep) {
         if (n != N) { set_error(std::string("short read ") + path); return CUDNS_EINVAL; }
     }
     return cudns_set_state(S, buf.data(), buf.data() + N, buf.data() + 2 * N, buf.data() + 3 * N, buf.data() + 4 * N);
+}
+
+}  // extern "C"
+
+
+// ---- on-device diagnostics of the channel / boundary-layer workflows -----------------------------
+static int prof_scratch(cudns_solver *S) {
+    if (S->d_prof) return CUDNS_OK;
+    return dmalloc(S, &S->d_prof, (size_t)profile_partial_doubles(S->kc) + 10 * (size_t)S->L.mx + 8);
+}
+
+extern "C" {
+
+// calcAvgChan, init.cpp:150-208
+int cudns_calc_profiles(cudns_handle S, double *prof) {
+    if (!S || !prof) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    int rc = prof_scratch(S); if (rc) return rc;
+    const int mx = S->L.mx;
+    double *partial = S->d_prof, *mean = partial + profile_partial_doubles(S->kc), *var = mean + 5 * mx;
+    const double scale = 1.0 / ((double)S->P.my * (double)S->P.mz);        // global row count: slabs add up to the whole plane
+    const double *q = S->state[S->cur];
+    launch_profile_partial(S->kc, q, nullptr, partial, 0, S->st);
+    launch_profile_combine(S->kc, partial, mean, scale, S->st);
+    reduce_across(S, mean, 5 * mx, 1);
+    launch_profile_favre(S->kc, mean, S->st);
+    launch_profile_partial(S->kc, q, mean, partial, 1, S->st);
+    launch_profile_combine(S->kc, partial, var, scale, S->st);
+    reduce_across(S, var, 5 * mx, 1);
+    S->launches += 5;
+    CK(cudaMemcpyAsync(prof, mean, 10 * (size_t)mx * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return CUDNS_OK;
+}
+
+// printRes, init.cpp:210-256 (the wall at i = 0; meaningful for the non-periodic-x set-ups)
+int cudns_calc_retau(cudns_handle S, double *retau) {
+    if (!S || !retau) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    int rc = prof_scratch(S); if (rc) return rc;
+    double *partial = S->d_prof, *out = partial + profile_partial_doubles(S->kc) + 10 * (size_t)S->L.mx;
+    launch_retau(S->kc, S->state[S->cur], partial, out, 1.0 / ((double)S->P.my * (double)S->P.mz), S->st);
+    reduce_across(S, out, 1, 1);
+    S->launches += 2;
+    CK(cudaMemcpyAsync(retau, out, sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    return CUDNS_OK;
 }
 
 }  // extern "C"

@@ -13,9 +13,6 @@ namespace cudns {
 constexpr int GX = 4;            // x ghost width in memory (>= s, even: keeps interior rows 16B aligned)
 constexpr int MAXS = 4;
 
-// quantities staged on chip by the RHS kernel
-enum { QR = 0, QU, QV, QW, QH, QP, QT, QM, QD, NQ };
-
 // Padded ghost-cell layout of one field: [pz][py][px], x fastest.
 struct Layout {
     int mx, my, mz;              // local interior extents (mz = this rank's slab)
@@ -86,9 +83,6 @@ struct StagePtrs {
 struct StageMaps {
     CUtensorMap qbox, qint, thbox, thint;
 };
-#ifndef STAGE_TY
-#define STAGE_TY 8              // tile rows of the stage kernel (= warps per CTA)
-#endif
 // ---- lean stage kernel (stage_lean.inc): tile rows per CTA for the linear-viscosity (8 quantities) and the general
 // (9 quantities) variants, and its TMA descriptors
 #ifndef CUDNS_LEAN_TY_LINEAR
@@ -118,12 +112,8 @@ int fast_smem_bytes(int s, int ty);
 int lean_smem_wide_bytes(int s);
 #define CUDNS_LEAN_TY_WIDE 16
 int lean_smem_bytes(int s, bool linear_visc);
-int stage_tile_y();
-int stage_smem_bytes(int s, bool linear_visc);
 
 void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st);
-void launch_rhs_stage(const KConst &kc, const StagePtrs &p, const StageCoef &c, const StageMaps &maps, cudaStream_t st);
-void launch_rhs_stage_smem(const KConst &kc, const StagePtrs &p, const StageCoef &c, cudaStream_t st);
 void launch_fill_xy(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_zwrap(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_pack_z(const KConst &kc, const double *q5, double *send_lo, double *send_hi, cudaStream_t st);
@@ -134,11 +124,16 @@ void launch_unpad(const KConst &kc, const double *q5, double *dst5[5], cudaStrea
 void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st);
 void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st);
 void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
+// wall-normal profiles / friction Reynolds number (calcAvgChan, printRes): see kernels.cu
+void launch_profile_partial(const KConst &kc, const double *q, const double *mean, double *partial, int pass, cudaStream_t st);
+void launch_profile_combine(const KConst &kc, const double *partial, double *out, double scale, cudaStream_t st);
+void launch_profile_favre(const KConst &kc, double *mean, cudaStream_t st);
+int profile_partial_doubles(const KConst &kc);
+void launch_retau(const KConst &kc, const double *q, double *partial, double *out, double scale, cudaStream_t st);
 // cross-GPU stage hand-shake over peer memory: store `epoch` into the two neighbours' mailbox slots / spin until both own slots reach it
 void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st);
 void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, cudaStream_t st);
 
-int rhs_stage_smem_bytes(int s);
 bool rhs_stage_supported(int s, int v);
 
 void set_error(const std::string &msg);

@@ -193,6 +193,13 @@ int cudns_io_wait(cudns_handle h, uint64_t *files_written);
  * rank reads its own slab */
 int cudns_read_fields(cudns_handle h, const char *dir, int timestep);
 
+/* ---- on-device diagnostics: no copyField(1) + host loops ------------------------------------------
+ * calcAvgChan (init.cpp:150-208): prof[10][mx] (host) = y-z means per wall-normal index of rho, Favre-averaged u, v, w, rho E
+ * (rows 0-4) and the mean squares of rho, u, v, w, rho E about them (rows 5-9): the columns 2-11 of the reference's prof.txt. */
+int cudns_calc_profiles(cudns_handle h, double *prof);
+/* printRes (init.cpp:210-256): average friction Reynolds number of the wall at i = 0 */
+int cudns_calc_retau(cudns_handle h, double *retau);
+
 #ifdef __cplusplus
 }
 #endif

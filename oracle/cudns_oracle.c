@@ -735,6 +735,61 @@ void ora_calc_bulk(ora_solver *S, double *par1, double *par2) {
     }
 }
 
+/* calcAvgChan init.cpp:150-208: y-z averages per wall-normal index i.  prof[0..4][i] = <rho>, <rho u>/<rho>, <rho v>/<rho>,
+ * <rho w>/<rho>, <rho E>; prof[5..9][i] = mean squares of (rho, u, v, w, rho E) about those means (prof.txt columns 2..11) */
+void ora_calc_profiles(ora_solver *S, double *prof) {
+    const int mx = S->mx, my = S->my, mz = S->mz;
+    double *rm = prof, *um = prof + mx, *vm = prof + 2*mx, *wm = prof + 3*mx, *em = prof + 4*mx;
+    double *rf = prof + 5*mx, *uf = prof + 6*mx, *vf = prof + 7*mx, *wf = prof + 8*mx, *ef = prof + 9*mx;
+    for (int i = 0; i < mx; i++) {
+        rm[i] = um[i] = vm[i] = wm[i] = em[i] = 0.0; rf[i] = uf[i] = vf[i] = wf[i] = ef[i] = 0.0;
+        for (int k = 0; k < mz; k++)
+            for (int j = 0; j < my; j++) {
+                size_t g = (size_t)i + (size_t)j*mx + (size_t)k*mx*my;
+                rm[i] += S->r[g]/my/mz;
+                um[i] += S->r[g]*S->u[g]/my/mz;
+                vm[i] += S->r[g]*S->v_[g]/my/mz;
+                wm[i] += S->r[g]*S->w[g]/my/mz;
+                em[i] += S->e[g]/my/mz;
+            }
+    }
+    for (int i = 0; i < mx; i++) {
+        um[i] /= rm[i]; vm[i] /= rm[i]; wm[i] /= rm[i];
+        for (int k = 0; k < mz; k++)
+            for (int j = 0; j < my; j++) {
+                size_t g = (size_t)i + (size_t)j*mx + (size_t)k*mx*my;
+                rf[i] += (S->r[g]-rm[i])*(S->r[g]-rm[i])/my/mz;
+                uf[i] += (S->u[g]-um[i])*(S->u[g]-um[i])/my/mz;
+                vf[i] += (S->v_[g]-vm[i])*(S->v_[g]-vm[i])/my/mz;
+                wf[i] += (S->w[g]-wm[i])*(S->w[g]-wm[i])/my/mz;
+                ef[i] += (S->e[g]-em[i])*(S->e[g]-em[i])/my/mz;
+            }
+    }
+}
+
+/* printRes init.cpp:210-256: average friction Reynolds number of the wall at i = 0 (one-sided stencil on the anti-mirrored
+ * streamwise velocity w, wall temperature 1) */
+double ora_calc_retau(ora_solver *S) {
+    const int mx = S->mx, my = S->my, mz = S->mz, s = S->s;
+    double Ret = 0.0;
+    for (int k = 0; k < mz; k++)
+        for (int j = 0; j < my; j++) {
+            double temw = 1.0;
+            double suth = pow(temw, S->P.viscexp);
+            double muw = suth/S->P.Re;
+            double ub[2*4+1];
+            for (int i = s; i < s*2+1; i++) ub[i] = S->w[i-s + j*mx + (size_t)k*my*mx];
+            for (int i = 0; i < s; i++)     ub[i] = S->w[s-i-1 + j*mx + (size_t)k*my*mx];
+            double dudx = 0;
+            for (int i = 0; i < s; i++) dudx += S->cF[i]*(ub[i]-ub[s*2-i])/S->dx;
+            dudx *= S->xp[0];
+            size_t g0 = (size_t)j*mx + (size_t)k*mx*my;
+            double ut = sqrt(muw*fabs(dudx)/S->r[g0]);       /* the reference calls the integer abs(); fabs is what is meant */
+            Ret += ut*S->r[g0]/muw;
+        }
+    return Ret/my/mz;
+}
+
 /* calcTimeStepPressGrad cuda_main.cu:249-265, calcPressureGrad calc_stress.cu:98-120 */
 static void calcTimeStepPressGrad(ora_solver *S) {
     if (!S->fixed_dt) S->dtC = ora_calc_dt(S);

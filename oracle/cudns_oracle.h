@@ -114,6 +114,10 @@ void ora_calc_rhs(ora_solver *s, double *rhs[5]);
 double ora_calc_dt(ora_solver *s);
 /* calcBulk (calc_stress.cu:162-201) */
 void ora_calc_bulk(ora_solver *s, double *par1, double *par2);
+/* calcAvgChan init.cpp:150-208: prof[10][mx] = y-z means (rho, Favre u,v,w, rho E) and mean squares about them */
+void ora_calc_profiles(ora_solver *s, double *prof);
+/* printRes init.cpp:210-256: average friction Reynolds number at the wall i = 0 */
+double ora_calc_retau(ora_solver *s);
 
 /* runSimulationLowStorage / runSimulation (cuda_main.cu:44-186): advance nsteps steps
  * ("one file").  time/par1/par2 may be NULL or arrays of nsteps entries (par entries are

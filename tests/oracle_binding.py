@@ -67,6 +67,8 @@ def lib():
         L.ora_calc_rhs.argtypes = [C.c_void_p, C.POINTER(dp)]
         L.ora_calc_dt.argtypes = [C.c_void_p]; L.ora_calc_dt.restype = C.c_double
         L.ora_calc_bulk.argtypes = [C.c_void_p, dp, dp]
+        L.ora_calc_profiles.argtypes = [C.c_void_p, dp]
+        L.ora_calc_retau.argtypes = [C.c_void_p]; L.ora_calc_retau.restype = C.c_double
         L.ora_run.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
         for name in ("ora_get_dt", "ora_get_dpdz", "ora_get_time"):
             f = getattr(L, name); f.argtypes = [C.c_void_p]; f.restype = C.c_double
@@ -199,6 +201,13 @@ class Oracle:
         a = C.c_double(0.0); b = C.c_double(0.0)
         self.L.ora_calc_bulk(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def profiles(self):
+        out = np.zeros((10, self.p.mx))
+        self.L.ora_calc_profiles(self.h, _dp(out))
+        return out
+
+    def retau(self): return self.L.ora_calc_retau(self.h)
 
     def run(self, nsteps):
         t = np.zeros(nsteps); p1 = np.full(nsteps, np.nan); p2 = np.full(nsteps, np.nan)
