@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDNS_LIB", os.path.join(_HERE, "libcudns.so"))   # o
 CSRC = os.path.join(_HERE, "csrc")
 
 __all__ = ["Params", "PeerInfo", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",
-           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "write_xdmf", "EXPORTS"]
+           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "write_xdmf", "blasius_profiles", "EXPORTS"]
 
 # every symbol include/cudns.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -31,7 +31,7 @@ EXPORTS = [
     "cudns_halo_local_info", "cudns_halo_connect", "cudns_halo_buffers", "cudns_set_allreduce",
     "cudns_set_exchange", "cudns_get_stream", "cudns_get_counters", "cudns_profile_stage",
     "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
-    "cudns_calc_profiles", "cudns_calc_retau",
+    "cudns_calc_profiles", "cudns_calc_retau", "cudns_blasius_profiles",
 ]
 
 
@@ -135,6 +135,7 @@ def lib():
     L.cudns_profile_stage.argtypes = [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.cudns_write_fields_async.argtypes = [H, C.c_char_p, C.c_int]
     L.cudns_calc_profiles.argtypes = [H, dp]
+    L.cudns_blasius_profiles.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp, dp]
     L.cudns_calc_retau.argtypes = [H, dp]
     L.cudns_io_wait.argtypes = [H, C.POINTER(C.c_uint64)]
     L.cudns_read_fields.argtypes = [H, C.c_char_p, C.c_int]
@@ -217,6 +218,13 @@ def read_field(directory, name, timestep, shape):
     a = np.zeros(shape)
     _check(lib().cudns_read_field(directory.encode(), name.encode(), timestep, _dp(a), a.size))
     return a
+
+
+def blasius_profiles(gam=1.4, Ma=0.35, Pr=0.75, n=1000):
+    """(x, r, u, w, e) similarity profiles of the boundary-layer inflow (python-utils/selfSimilarSol.py)"""
+    out = [np.zeros(n) for _ in range(5)]
+    _check(lib().cudns_blasius_profiles(gam, Ma, Pr, n, *[_dp(a) for a in out]))
+    return out
 
 
 def write_xdmf(path, x, y, z, timesteps, dt, names="ruvwe", single_precision=False):

@@ -275,6 +275,75 @@ int cudns_read_field(const char *dir, char name, int timestep, double *var, size
 }
 
 
+// Compressible self-similar boundary layer (python-utils/selfSimilarSol.py:1-98): the inflow / sponge reference profiles of the
+// boundary-layer case without Python.  Same equations, boundary conditions, eta range [0,10] on 600 points and post-processing
+// as the reference script (which solves the boundary-value problem with scipy's collocation solver at its default 1e-3
+// tolerance); here: shooting on (F''(0), h(0)) with classical RK4 (6000 steps) and Newton, converged to 1e-13.
+//   F0' = F1, F1' = F2/C, F2' = -F0 F2/C, h' = G1 Pr/C, G1' = -(F0 G1 Pr + Ec F2^2)/C, y' = sqrt(2) h,   C = h^(expMu-1)
+//   F0(0) = F1(0) = G1(0) = y(0) = 0 (adiabatic wall), F1(10) = h(10) = 1.
+// Outputs (n entries each, the reference writes n = 1000): x = wall distance / delta_99, r = density, u = wall-normal velocity,
+// w = streamwise velocity, e = internal energy T Rgas/(gam-1); beyond the 600 computed points the free stream continues with
+// steps of 0.15.  Like the reference script the viscosity exponent is fixed at 3/2 whatever the caller's viscexp is.
+int cudns_blasius_profiles(double gam, double Ma, double Pr, int n, double *x, double *r, double *u, double *w, double *e) {
+    if (!x || !r || !u || !w || !e || n < 600) { set_error("cudns_blasius_profiles: NULL output or n < 600"); return CUDNS_EINVAL; }
+    const double expMu = 1.5, Ec = (gam - 1.0) * Ma * Ma, Rgas = 1.0 / (gam * Ma * Ma);
+    const int NP = 600, SUB = 10, NS = (NP - 1) * SUB;
+    const double h = 10.0 / NS;
+    auto rhs = [&](const double *f, double *d) {
+        const double C = std::pow(f[3], expMu - 1.0);
+        d[0] = f[1]; d[1] = f[2] / C; d[2] = -f[0] * f[2] / C; d[3] = f[4] * Pr / C;
+        d[4] = -f[0] * f[4] * Pr / C - Ec * f[2] * f[2] / C; d[5] = std::sqrt(2.0) * f[3];
+    };
+    std::vector<double> sol((size_t)NP * 6);
+    auto shoot = [&](double a, double b, double *res) {
+        double f[6] = {0.0, 0.0, a, b, 0.0, 0.0};
+        for (int m = 0; m < 6; m++) sol[m] = f[m];
+        for (int st = 0; st < NS; st++) {
+            double k1[6], k2[6], k3[6], k4[6], t[6];
+            rhs(f, k1);
+            for (int m = 0; m < 6; m++) t[m] = f[m] + 0.5 * h * k1[m];
+            rhs(t, k2);
+            for (int m = 0; m < 6; m++) t[m] = f[m] + 0.5 * h * k2[m];
+            rhs(t, k3);
+            for (int m = 0; m < 6; m++) t[m] = f[m] + h * k3[m];
+            rhs(t, k4);
+            for (int m = 0; m < 6; m++) f[m] += h / 6.0 * (k1[m] + 2.0 * k2[m] + 2.0 * k3[m] + k4[m]);
+            if ((st + 1) % SUB == 0) for (int m = 0; m < 6; m++) sol[(size_t)((st + 1) / SUB) * 6 + m] = f[m];
+        }
+        res[0] = f[1] - 1.0; res[1] = f[3] - 1.0;
+    };
+    double a = 0.47, b = 1.0 + 0.5 * std::sqrt(Pr) * Ec, res[2];
+    bool ok = false;
+    for (int it = 0; it < 50; it++) {
+        shoot(a, b, res);
+        if (std::fabs(res[0]) < 1e-13 && std::fabs(res[1]) < 1e-13) { ok = true; break; }
+        const double da = 1e-7, db = 1e-7;
+        double ra[2], rb[2];
+        shoot(a + da, b, ra); shoot(a, b + db, rb);
+        const double J00 = (ra[0] - res[0]) / da, J10 = (ra[1] - res[1]) / da, J01 = (rb[0] - res[0]) / db, J11 = (rb[1] - res[1]) / db;
+        const double det = J00 * J11 - J01 * J10;
+        if (!(std::fabs(det) > 1e-300)) break;
+        a -= (J11 * res[0] - J01 * res[1]) / det;
+        b -= (-J10 * res[0] + J00 * res[1]) / det;
+    }
+    if (!ok) { shoot(a, b, res); ok = std::fabs(res[0]) < 1e-10 && std::fabs(res[1]) < 1e-10; }
+    if (!ok) { set_error("cudns_blasius_profiles: shooting did not converge"); return CUDNS_EINVAL; }
+    shoot(a, b, res);
+    int idx = -1;
+    for (int i = 0; i < NP; i++) if (sol[(size_t)i * 6 + 1] > 0.99) { idx = i; break; }
+    if (idx < 0) { set_error("cudns_blasius_profiles: no point with U > 0.99"); return CUDNS_EINVAL; }
+    const double delta = sol[(size_t)idx * 6 + 5];
+    for (int i = 0; i < NP; i++) {
+        const double F0 = sol[(size_t)i * 6], U = sol[(size_t)i * 6 + 1], T = sol[(size_t)i * 6 + 3], yb = sol[(size_t)i * 6 + 5];
+        const double rho = 1.0 / T;
+        x[i] = yb / delta; r[i] = rho; w[i] = U;
+        u[i] = (U * yb / std::sqrt(4.0) - F0 / (rho * std::sqrt(2.0))) / delta;
+        e[i] = T * Rgas / (gam - 1.0);
+    }
+    for (int i = NP; i < n; i++) { x[i] = x[i - 1] + 0.15; r[i] = r[NP - 1]; u[i] = u[NP - 1]; w[i] = w[NP - 1]; e[i] = e[NP - 1]; }
+    return CUDNS_OK;
+}
+
 // XDMF 2.0 sidecar for the fields/ directory (what python-utils/writexmf.py + makexmf.py produce): a 3DRectMesh with the VXVYVZ
 // coordinates inline, one temporal collection, one uniform grid per saved time step whose attributes point at <name>.<%07d>.bin.
 // names: one character per field ("ruvwe"); time of step t = t * dt.

@@ -93,6 +93,10 @@ int cudns_build_sponge(const cudns_params *p, const double *x, const double *z,
                        const double *xIn, const double *rIn, const double *uIn, const double *wIn, int n,
                        double *sigma_x, double *sigma_z, double *ref5,
                        double *r, double *u, double *v, double *w, double *e);
+/* python-utils/selfSimilarSol.py:1-98 without Python: compressible self-similar (Blasius) boundary-layer profiles for
+ * cudns_build_sponge -- x = wall distance / delta_99, r, u (wall-normal), w (streamwise), e = T Rgas/(gam-1); n >= 600 entries
+ * each (the reference's blasius1D/{x,r,u,w,e}Prof.bin hold n = 1000).  Shooting + RK4 instead of scipy.solve_bvp. */
+int cudns_blasius_profiles(double gam, double Ma, double Pr, int n, double *x, double *r, double *u, double *w, double *e);
 /* writeField / initField (init.cpp:13-30 -> comm.cpp:205-279): fields/<c>.<%07d>.bin, raw float64,
  * [mz_tot][my_tot][mx_tot], no header.  dir is the directory that contains "fields". */
 int cudns_write_field(const char *dir, char name, int timestep, const double *var, size_t count);
