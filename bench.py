@@ -239,6 +239,10 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     c1 = sol.counters()
+    if dist is not None:                                           # max over ranks (also: every rank must derive the same `extra`)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     # nvidia-smi delivers a sample every ~100 ms: when the timed region was shorter than that (many GPUs, small K), the same
     # workload keeps running untimed until the sampler has seen it for ~0.8 s, so the clocks line describes this load
     extra = 0
@@ -249,10 +253,6 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["covers"] = "timed region" if extra == 0 else "timed region + %d untimed steps of the same workload" % extra
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     npts = float(n) ** 3
     value = npts * stages * args.steps / (ms * 1e-3) / 1e6          # Mpts*stage/s, whole job
     launches = int(c1["kernel_launches"] - c0["kernel_launches"])
