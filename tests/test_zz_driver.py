@@ -1,0 +1,74 @@
+"""cudns_run, the C++ host driver on top of the C ABI (main.cpp + solverWrapper of the reference).
+
+CPU: --dry-run (configuration, grid files, initial condition, file 0, XDMF) against the library's own host functions.
+GPU: the channel golden of the reference's own GPU binary re-run through the driver (restart from its file 0, two output files of
+ten steps): fields and solution.txt rows.  The driver calls the on-device diagnostics that have not been seen on hardware yet, so
+the GPU test is xfail(strict=False) like tests/test_zz_diagnostics.py."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cudanavierstokes_b200 as cd
+from common import CONFIGS, conserved, load_golden, relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "cudanavierstokes_b200", "cudns_run")
+
+
+def _run(args, **kw):
+    cd.build()
+    return subprocess.run([EXE] + args, capture_output=True, text=True, timeout=600, **kw)
+
+
+def test_dry_run_writes_grid_and_initial_condition(tmp_path):
+    out = tmp_path / "run"
+    r = _run(["case=tgv", "mx=16", "my=16", "mz=16", "stencilSize=3", "Re=400", "outdir=%s" % out, "--dry-run"])
+    assert r.returncode == 0, r.stderr
+    p = cd.params_tgv(16, 3, Re=400.0); g = cd.init_grid(p)
+    for c in "xyz":
+        assert np.array_equal(np.fromfile(out / "fields" / ("%s.bin" % c)), g[c])
+    for c, a in zip("ruvwe", cd.init_chit(p, g)):
+        assert np.array_equal(np.fromfile(out / "fields" / ("%s.0000000.bin" % c)).reshape(a.shape), a)
+    rows = np.loadtxt(out / "Grid.txt")
+    assert rows.shape == (16, 4) and np.allclose(rows[:, 1], g["x"], atol=5e-7)       # "%lf": six decimals
+    assert (out / "fields" / "fields.xmf").read_text().count("<Attribute") == 5
+
+
+def test_config_file_and_errors(tmp_path):
+    cfg = tmp_path / "run.cfg"
+    cfg.write_text("# boundary layer, small\ncase = blayer\nmx = 48   # wall-normal\nmy=16\nmz=192\noutdir = %s\n" % (tmp_path / "bl"))
+    r = _run([str(cfg), "--dry-run"])
+    assert r.returncode == 0 and "case blayer  grid 48 x 16 x 192" in r.stdout, r.stderr
+    assert (tmp_path / "bl" / "fields" / "r.0000000.bin").stat().st_size == 48 * 16 * 192 * 8
+    r = _run(["nosuchkey=3", "--dry-run"])
+    assert r.returncode != 0 and "unknown key" in r.stderr
+    r = _run(["case=tgv", "mx=16", "my=16", "mz=16", "stencilSize=2", "stencilVisc=3", "outdir=%s" % (tmp_path / "bad")])
+    assert r.returncode != 0                         # invalid stencil pair (or no GPU): never a silent success
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="driver + on-device diagnostics not yet seen on hardware (round-1 GPU budget exhausted)")
+def test_driver_reproduces_the_reference_channel_run(tmp_path):
+    name = "chan_s3v2"
+    cfg = CONFIGS[name]; g = load_golden(name)
+    out = tmp_path / "run"
+    os.makedirs(out / "fields")
+    for c, a in zip("ruvwe", g["file0"]):
+        np.ascontiguousarray(a).tofile(out / "fields" / ("%s.0000000.bin" % c))
+    keys = ("mx", "my", "mz", "stencilSize", "stencilVisc", "Lx", "Ly", "Lz", "CFL", "checkCFLcondition", "checkBulk", "Re", "Pr", "Ma",
+            "viscexp", "stretch", "forcing", "periodicX", "nonUniformX", "lowStorage")
+    args = ["case=channel", "restartFile=0", "nfiles=2", "nsteps=%d" % cfg["nsteps"], "outdir=%s" % out, "async_io=1"]
+    args += ["%s=%r" % (k, cfg[k]) for k in keys]
+    r = _run(args)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = [np.fromfile(out / "fields" / ("%s.0000002.bin" % c)).reshape(g["file2"][0].shape) for c in "ruvwe"]
+    errs = [relerr(a, b) for a, b in zip(conserved(got), conserved(list(g["file2"])))]
+    assert max(errs) < 5e-12, errs
+    sol = np.loadtxt(out / "solution.txt")
+    assert sol.shape == g["solution"].shape
+    assert np.array_equal(sol[:, 0], g["solution"][:, 0])
+    assert np.allclose(sol[:, 1:], g["solution"][:, 1:], rtol=0, atol=2e-6)          # "%lf": six decimals on both sides
+    prof = np.loadtxt(out / "prof.txt")
+    assert prof.shape == (cfg["mx"], 11) and np.isfinite(prof).all()
