@@ -1,15 +1,15 @@
 """Wall-normal profiles and friction Reynolds number (calcAvgChan init.cpp:150-208, printRes :210-256).
 
 CPU: the oracle's restatement against a vectorised numpy formulation of the same definitions.
-GPU: libcudns (on-device reductions) against the oracle.  The device implementation was written after the round's GPU budget had
-run out, so the GPU tests are marked xfail(strict=False) until they have been seen passing on hardware (this file sorts last:
-nothing runs after it in the same process)."""
+GPU: libcudns (on-device reductions) against the oracle, in a process of its own (tools/check_diagnostics.py).  The device
+implementation was written after the round's GPU budget had run out, so the GPU test is marked xfail(strict=False) until it has
+been seen passing on hardware."""
 import numpy as np
 import pytest
 
 import cudanavierstokes_b200 as cd
 import oracle_binding as ob
-from common import CONFIGS, apply_cfg, make_pair, smooth_random_state
+from common import CONFIGS, apply_cfg
 
 COEFF_F = {1: [-0.5], 2: [1 / 12, -2 / 3], 3: [-1 / 60, 3 / 20, -3 / 4], 4: [1 / 280, -4 / 105, 1 / 5, -4 / 5]}   # globals.h:69-82
 
@@ -49,29 +49,11 @@ def test_oracle_profiles_and_retau_match_numpy(name):
     assert abs(o.retau() - rt) <= 1e-12 * rt
 
 
-HW = pytest.mark.xfail(strict=False, reason="on-device diagnostics not yet seen on hardware (round-1 GPU budget exhausted)")
-
-
 @pytest.mark.gpu
-@HW
-@pytest.mark.parametrize("name", ["chan_s3v2", "chan_s2v2"])
-def test_device_profiles_and_retau_match_oracle(name):
-    op = apply_cfg(ob.params_tgv(16, 3), CONFIGS[name])
-    o, s, grid = make_pair(op)
-    o.init_channel(); s.set_state(o.state())
-    o.run(3); s.advance(3)
-    got = s.profiles(); ref = o.profiles()
-    for a, b in zip(got, ref):
-        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-30) + 1e-28
-    assert abs(s.retau() - o.retau()) <= 1e-11 * o.retau()
-
-
-@pytest.mark.gpu
-@HW
-def test_device_profiles_ragged_periodic_box():
-    op = ob.params_tgv(24, 3, mx=40, my=20, mz=24)
-    o, s, grid = make_pair(op)
-    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
-    got = s.profiles(); ref = o.profiles()
-    for a, b in zip(got, ref):
-        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-30) + 1e-28
+@pytest.mark.xfail(strict=False, reason="on-device diagnostics not yet seen on hardware (round-1 GPU budget exhausted)")
+def test_device_profiles_and_retau_match_oracle():
+    """channel (two stencil pairs, after 3 steps) and a ragged periodic box: tools/check_diagnostics.py in its own process"""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_diagnostics.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
