@@ -30,6 +30,7 @@ EXPORTS = [
     "cudns_calc_rhs", "cudns_calc_dt", "cudns_calc_bulk", "cudns_get_scalars", "cudns_set_dt",
     "cudns_halo_local_info", "cudns_halo_connect", "cudns_halo_buffers", "cudns_set_allreduce",
     "cudns_set_exchange", "cudns_get_stream", "cudns_get_counters", "cudns_profile_stage",
+    "cudns_set_stage_timing", "cudns_get_stage_timing",
     "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
     "cudns_calc_profiles", "cudns_calc_retau", "cudns_blasius_profiles",
 ]
@@ -133,6 +134,8 @@ def lib():
     L.cudns_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     L.cudns_get_counters.argtypes = [H, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.cudns_profile_stage.argtypes = [H, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cudns_set_stage_timing.argtypes = [H, C.c_int]
+    L.cudns_get_stage_timing.argtypes = [H, dp, dp, dp, C.POINTER(C.c_uint64)]
     L.cudns_write_fields_async.argtypes = [H, C.c_char_p, C.c_int]
     L.cudns_calc_profiles.argtypes = [H, dp]
     L.cudns_blasius_profiles.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp, dp]
@@ -367,6 +370,16 @@ class Solver:
         a = C.c_float(0); b = C.c_float(0); c = C.c_float(0)
         _check(self.L.cudns_profile_stage(self.h, reps, C.byref(a), C.byref(b), C.byref(c)))
         return dict(theta_ms=a.value, rhs_stage_ms=b.value, halo_ms=c.value)
+
+    def stage_timing(self, on=None):
+        """on=True/False: switch the per-stage event timing of advance() on (sums reset) / off; on=None: read the sums"""
+        if on is not None:
+            _check(self.L.cudns_set_stage_timing(self.h, int(bool(on))))
+            return None
+        a = C.c_double(0); b = C.c_double(0); c = C.c_double(0); n = C.c_uint64(0)
+        _check(self.L.cudns_get_stage_timing(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)))
+        k = max(int(n.value), 1)
+        return dict(stages=int(n.value), theta_ms=a.value / k, rhs_stage_ms=b.value / k, halo_ms=c.value / k)
 
     def halo_buffers(self):
         p = [C.c_void_p() for _ in range(4)]; n = C.c_size_t(0)

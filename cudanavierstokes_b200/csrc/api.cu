@@ -20,6 +20,16 @@ void launch_dt_combine(double *dt, const double *conv, const double *visc, doubl
 }
 using namespace cudns;
 
+// inside cudns_create, once the solver object exists: a failing CUDA call must not leak it
+#define CKC(call)                                                                                    \
+    do {                                                                                             \
+        cudaError_t err__ = (call);                                                                  \
+        if (err__ != cudaSuccess) {                                                                  \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(err__));                        \
+            cudns_destroy(S);                                                                        \
+            return CUDNS_ECUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
 #define CK(call)                                                                                     \
     do {                                                                                             \
         cudaError_t err__ = (call);                                                                  \
@@ -30,7 +40,8 @@ using namespace cudns;
     } while (0)
 
 // device scalar slots
-enum { SC_DT = 0, SC_DPDZ, SC_TGPU, SC_TIME, SC_RED0, SC_RED1, SC_STALE0, SC_STALE1, SC_BULK0, SC_BULK1, SC_BULK2, SC_BULK3, SC_N = 16 };
+enum { SC_DT = 0, SC_DPDZ, SC_TGPU, SC_TIME, SC_RED0, SC_RED1, SC_STALE0, SC_STALE1, SC_BULK0, SC_BULK1, SC_BULK2, SC_BULK3,
+       SC_HALOERR /* u64: stage number of a hand-shake that timed out, 0 = none */, SC_N = 16 };
 
 // asynchronous fields/ writer: one snapshot in flight
 struct IoState {
@@ -47,8 +58,19 @@ struct IoState {
     uint64_t files_written = 0;
 };
 
+// per-kernel device times of the step loop under its real (sustained, possibly power-capped) conditions: CUDA events around the
+// dilatation pass, the stage kernel and the hand-shake of every stage of a cudns_advance call, read back after its final sync
+struct StageTimer {
+    std::vector<cudaEvent_t> ev;        // 4 per stage
+    size_t used = 0;
+    double theta_ms = 0, stage_ms = 0, halo_ms = 0;
+    uint64_t n = 0;
+    bool on = false;
+};
+
 struct cudns_solver {
     IoState *io;
+    StageTimer *tm;
     cudns_params P;
     KConst kc;
     Layout L;
@@ -68,6 +90,8 @@ struct cudns_solver {
     double *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
     double *d_scal;
     double *d_hist; int hist_cap;
+    double *d_bulk;              // bulk_reduce_kernel scratch (block partials + completion counter), this solver's own
+    unsigned long long halo_timeout_ns;
     double *d_prof;              // profile diagnostics scratch: partial[64][5][mx], mean[5][mx], var[5][mx], 1 scalar (lazy)
     double *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
     bool have_state, fixed_dt, have_sponge;
@@ -161,7 +185,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     L.px = ((mx + 2 * GX + 15) / 16) * 16; L.py = my + 2 * s; L.pz = mzl + 2 * L.gz;
     L.plane = (size_t)L.px * L.py; L.vol = L.plane * L.pz;
     S->N = (size_t)mx * my * mzl;
-    CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
     S->nstate = (p->lowStorage && !p->rk4) ? 2 : 3;
     {   // the fourth-generation stage kernel (stage_fast.cu) applies to the periodic / uniform / linear-viscosity set-ups; its state
         // buffers carry three more padded fields (H, T, theta).  CUDNS_WIDE=0 / 1 select the older kernels (A/B timing)
@@ -174,16 +198,22 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     S->block_doubles = (size_t)S->nstate * S->nfb * L.vol;
     S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
     if ((rc = dmalloc(S, &S->block, S->block_doubles + 32))) { cudns_destroy(S); return rc; }
-    CK(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(double), S->st));
     for (int b = 0; b < S->nstate; b++) S->state[b] = S->block + (size_t)b * S->nfb * L.vol;
     if ((rc = dmalloc(S, &S->theta, L.vol))) { cudns_destroy(S); return rc; }
-    CK(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
     if ((rc = dmalloc(S, &S->R1, 5 * S->N))) { cudns_destroy(S); return rc; }
-    CK(cudaMemsetAsync(S->R1, 0, 5 * S->N * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->R1, 0, 5 * S->N * sizeof(double), S->st));
     if (!(p->lowStorage && !p->rk4)) { if ((rc = dmalloc(S, &S->R2, 5 * S->N))) { cudns_destroy(S); return rc; } }
     if ((rc = dmalloc(S, &S->d_xp, mx)) || (rc = dmalloc(S, &S->d_dxv, mx)) || (rc = dmalloc(S, &S->d_cVSx, (size_t)mx * (2 * v + 1))) ||
         (rc = dmalloc(S, &S->d_scal, SC_N)) || (rc = dmalloc(S, &S->d_spx, mx)) || (rc = dmalloc(S, &S->d_spz, mzl)) ||
-        (rc = dmalloc(S, &S->d_sref, 5 * (size_t)mx * mzl))) { cudns_destroy(S); return rc; }
+        (rc = dmalloc(S, &S->d_sref, 5 * (size_t)mx * mzl)) || (rc = dmalloc(S, &S->d_bulk, bulk_scratch_doubles()))) { cudns_destroy(S); return rc; }
+    CKC(cudaMemsetAsync(S->d_bulk, 0, bulk_scratch_doubles() * sizeof(double), S->st));
+    {   // a neighbour that never signals (crashed rank, different stage count) must not hang the device: see halo_wait_kernel
+        const char *te = getenv("CUDNS_HALO_TIMEOUT_MS");
+        const double ms = te ? atof(te) : 30000.0;
+        S->halo_timeout_ns = (unsigned long long)((ms > 0 ? ms : 30000.0) * 1e6);
+    }
     S->halo_doubles = 5 * (size_t)L.gz * L.plane;
     if (p->nranks > 1) {
         if ((rc = dmalloc(S, &S->send_lo, S->halo_doubles)) || (rc = dmalloc(S, &S->send_hi, S->halo_doubles)) ||
@@ -204,15 +234,18 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     for (int l = 1; l <= v; l++) { kc.aV[l] = -cVF[v - l]; kc.bV[l] = cVS[v - l]; }
     kc.bV[0] = cVS[v];
     for (int d = 0; d < 3; d++) {
-        for (int l = 1; l <= s; l++) { kc.cC[d][l] = -0.25 * kc.aF[l] * kc.d1[d]; kc.cP[d][l] = kc.aF[l] * kc.d1[d]; }
-        for (int l = 0; l <= v; l++) { kc.c1[d][l] = kc.aV[l] * kc.d1[d]; kc.c2[d][l] = kc.bV[l] * kc.d2[d]; }
+        // cC = -a_l/(4 dx_d) (split-form flux sums), cP = a_l/dx_d (pressure gradient, advective order), c1 = a_l/dx_d and
+        // c2 = b_l/dx_d^2 (viscous order)
+        double cC[MAXS + 1] = {0}, cP[MAXS + 1] = {0}, c2[MAXS + 1] = {0};
+        for (int l = 1; l <= s; l++) { cC[l] = -0.25 * kc.aF[l] * kc.d1[d]; cP[l] = kc.aF[l] * kc.d1[d]; }
+        for (int l = 0; l <= v; l++) { kc.c1[d][l] = kc.aV[l] * kc.d1[d]; c2[l] = kc.bV[l] * kc.d2[d]; }
         for (int l = 0; l <= MAXS; l++) {
-            kc.cf[d][l][0] = kc.cC[d][l]; kc.cf[d][l][1] = -kc.cP[d][l]; kc.cf[d][l][2] = kc.c1[d][l]; kc.cf[d][l][3] = kc.c2[d][l];
+            kc.cf[d][l][0] = cC[l]; kc.cf[d][l][1] = -cP[l]; kc.cf[d][l][2] = kc.c1[d][l]; kc.cf[d][l][3] = c2[l];
             kc.c1t[d][l] = kc.c1[d][l] / 3.0;
         }
-        if (d == 2) for (int l = 0; l <= MAXS; l++) kc.cfzp[l] = -kc.cP[2][l] * (1.f / (p->gam * p->Ma * p->Ma));
-        for (int l = 0; l <= MAXS; l++) kc.cfp[d][l] = -kc.cP[d][l] * (1.f / (p->gam * p->Ma * p->Ma));
-        kc.c20sum += kc.c2[d][0];
+        if (d == 2) for (int l = 0; l <= MAXS; l++) kc.cfzp[l] = -cP[l] * (1.f / (p->gam * p->Ma * p->Ma));
+        for (int l = 0; l <= MAXS; l++) kc.cfp[d][l] = -cP[l] * (1.f / (p->gam * p->Ma * p->Ma));
+        kc.c20sum += c2[0];
     }
     kc.gam = p->gam;
     kc.Rgas = (1.f / (p->gam * p->Ma * p->Ma));                 // globals.h:48
@@ -240,16 +273,16 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         for (int it = v + 1; it < 2 * v + 1; it++)
             for (int i = 0; i < mx; i++)
                 tab[i + (size_t)it * mx] = (cVS[2 * v - it] * (xp[i] * xp[i]) * h_d2x + cVF[2 * v - it] * xpp[i] * (xp[i] * xp[i] * xp[i]) * h_dx);
-        CK(cudaMemcpy(S->d_dxv, dxv.data(), mx * sizeof(double), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(S->d_cVSx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(S->d_xp, xp, mx * sizeof(double), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(S->d_dxv, dxv.data(), mx * sizeof(double), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(S->d_cVSx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(S->d_xp, xp, mx * sizeof(double), cudaMemcpyHostToDevice));
     }
     kc.xp = S->d_xp; kc.cVSx = S->d_cVSx; kc.dxv = S->d_dxv;
     kc.spongeX = nullptr; kc.spongeZ = nullptr; kc.sref = nullptr;
     kc.dt = S->d_scal + SC_DT; kc.dpdz = S->d_scal + SC_DPDZ; kc.time_on_gpu = S->d_scal + SC_TGPU;
     double sc0[SC_N]; std::memset(sc0, 0, sizeof(sc0));
     sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
-    CK(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
+    CKC(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
     if ((size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
@@ -287,7 +320,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             if ((rc = make_rmap(&S->wrmap[0], L, S->R1, wty)) || (S->R2 && (rc = make_rmap(&S->wrmap[1], L, S->R2, wty)))) { cudns_destroy(S); return rc; }
         }
     }
-    CK(cudaStreamSynchronize(S->st));
+    CKC(cudaStreamSynchronize(S->st));
     *out = S;
     return CUDNS_OK;
 }
@@ -304,8 +337,9 @@ int cudns_destroy(cudns_handle S) {
     cudaFree(S->block);
     cudaFree(S->theta); cudaFree(S->R1); cudaFree(S->R2);
     cudaFree(S->d_xp); cudaFree(S->d_cVSx); cudaFree(S->d_dxv); cudaFree(S->d_spx); cudaFree(S->d_spz); cudaFree(S->d_sref);
-    cudaFree(S->d_scal); cudaFree(S->d_hist); cudaFree(S->d_prof);
+    cudaFree(S->d_scal); cudaFree(S->d_hist); cudaFree(S->d_prof); cudaFree(S->d_bulk);
     cudaFree(S->send_lo); cudaFree(S->send_hi); cudaFree(S->recv_lo); cudaFree(S->recv_hi);
+    if (S->tm) { for (auto &e : S->tm->ev) cudaEventDestroy(e); delete S->tm; }
     if (S->st) cudaStreamDestroy(S->st);
     delete S;
     return CUDNS_OK;
@@ -408,11 +442,26 @@ static int fill_z_ghosts(cudns_solver *S, double *q) {
 static void reduce_across(cudns_solver *S, double *dptr, int n, int op) {
     if (S->P.nranks > 1 && S->allreduce) S->allreduce(S->allreduce_user, dptr, n, op);
 }
+// every entry point that reduces scalars across the slabs (dt MAX, bulk / forcing / profile SUMs) refuses to run without the
+// collective: slabs advancing with rank-local dt or dpdz would produce a wrong answer silently
+static int need_allreduce(cudns_solver *S) {
+    if (S->P.nranks > 1 && !S->allreduce) { set_error("nranks > 1 needs the scalar all-reduce: call cudns_set_allreduce first"); return CUDNS_ESTATE; }
+    return CUDNS_OK;
+}
+// did a halo hand-shake of this solver give up waiting for a neighbour?  (call after the stream has been synchronised)
+static int check_halo_error(cudns_solver *S) {
+    if (S->P.nranks == 1) return CUDNS_OK;
+    unsigned long long e = 0;
+    if (cudaMemcpy(&e, S->d_scal + SC_HALOERR, sizeof(e), cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("reading the hand-shake status failed"); return CUDNS_ECUDA; }
+    if (e) { set_error("halo hand-shake timed out at stage " + std::to_string(e) + ": a slab neighbour did not signal (different stage count, or it died)"); return CUDNS_ESTATE; }
+    return CUDNS_OK;
+}
 
 extern "C" {
 
 int cudns_set_state_device(cudns_handle S, const double *d_r, const double *d_u, const double *d_v, const double *d_w, const double *d_e) {
     if (!S || !d_r || !d_u || !d_v || !d_w || !d_e) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
     CK(cudaSetDevice(S->P.device));
     const double *src[5] = {d_r, d_u, d_v, d_w, d_e};
     S->cur = 0;
@@ -552,7 +601,7 @@ static void handshake(cudns_solver *S) {
     unsigned long long *lo_slot = has_lo ? (unsigned long long *)(S->peer_lo + S->block_doubles) + 1 : nullptr;
     unsigned long long *hi_slot = has_hi ? (unsigned long long *)(S->peer_hi + S->block_doubles) + 0 : nullptr;
     launch_halo_signal(lo_slot, hi_slot, S->epoch, S->st);
-    launch_halo_wait(mine, has_lo, has_hi, S->epoch, S->st);
+    launch_halo_wait(mine, has_lo, has_hi, S->epoch, S->halo_timeout_ns, (unsigned long long *)(S->d_scal + SC_HALOERR), S->st);
     S->launches += 2;
 }
 
@@ -561,13 +610,18 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
                      const StageCoef &c, double *rhs_out) {
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
-    p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out; p.viscmax = nullptr;
+    p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out;
     const bool fast = stage_is_fast(S, p, c);
     if (fast) p.theta = S->state[in] + 7 * S->L.vol;            // 8-field buffers: theta travels with the state it belongs to
+    StageTimer *tm = (S->tm && S->tm->on && !rhs_out && S->tm->used + 4 <= S->tm->ev.size()) ? S->tm : nullptr;
+    cudaEvent_t *tev = tm ? &tm->ev[tm->used] : nullptr;
+    if (tm) { tm->used += 4; cudaEventRecord(tev[0], S->st); }
     launch_theta(S->kc, S->state[in], const_cast<double *>(p.theta), S->st);
+    if (tm) cudaEventRecord(tev[1], S->st);
     ghost_targets(S, out, p);
     if (rhs_out) { p.qout_lo = nullptr; p.qout_hi = nullptr; }
     launch_stage_any(S, p, c, in, base);
+    if (tm) cudaEventRecord(tev[2], S->st);
     S->launches += 2;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("stage launch: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
@@ -577,9 +631,23 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
         S->aux_valid[out] = fast && inkernel_ghosts(S);
         if (inkernel_ghosts(S)) handshake(S);
         else { int rc = fill_z_ghosts(S, S->state[out]); if (rc) return rc; }
+        if (tm) cudaEventRecord(tev[3], S->st);
         S->stages++;
     }
     return CUDNS_OK;
+}
+
+// after the stream has been synchronised: fold the recorded events into the running sums
+static void stage_timer_collect(cudns_solver *S) {
+    StageTimer *tm = S->tm;
+    if (!tm || !tm->on) return;
+    for (size_t i = 0; i + 4 <= tm->used; i += 4) {
+        float a = 0, b = 0, c = 0;
+        if (cudaEventElapsedTime(&a, tm->ev[i], tm->ev[i + 1]) != cudaSuccess || cudaEventElapsedTime(&b, tm->ev[i + 1], tm->ev[i + 2]) != cudaSuccess ||
+            cudaEventElapsedTime(&c, tm->ev[i + 2], tm->ev[i + 3]) != cudaSuccess) { cudaGetLastError(); continue; }
+        tm->theta_ms += a; tm->stage_ms += b; tm->halo_ms += c; tm->n++;
+    }
+    tm->used = 0;
 }
 
 // viscous limiter of the state the LAST calcState saw (the reference refreshes dt with the mu field left by the
@@ -612,6 +680,7 @@ int cudns_calc_rhs(cudns_handle S, double *rhs_r, double *rhs_u, double *rhs_v, 
 int cudns_calc_dt(cudns_handle S, double *dt) {
     if (!S || !dt) { set_error("NULL argument"); return CUDNS_EINVAL; }
     if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
     CK(cudaSetDevice(S->P.device));
     launch_dt_reduce(S->kc, S->state[S->cur], S->d_scal + SC_RED0, S->st); S->launches++;
     reduce_across(S, S->d_scal + SC_RED0, 2, 2);
@@ -625,8 +694,9 @@ int cudns_calc_dt(cudns_handle S, double *dt) {
 int cudns_calc_bulk(cudns_handle S, double *par1, double *par2) {
     if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
     if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
     CK(cudaSetDevice(S->P.device));
-    launch_bulk_reduce(S->kc, S->state[S->cur], S->d_scal + SC_BULK0, S->st); S->launches++;
+    launch_bulk_reduce(S->kc, S->state[S->cur], S->d_scal + SC_BULK0, S->d_bulk, S->st); S->launches++;
     reduce_across(S, S->d_scal + SC_BULK0, 4, 1);
     double h[4];
     CK(cudaStreamSynchronize(S->st));
@@ -642,14 +712,16 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
     if (!S->have_state) { set_error("cudns_advance before cudns_set_state"); return CUDNS_ESTATE; }
     if (nsteps < 0) { set_error("nsteps < 0"); return CUDNS_EINVAL; }
     if (S->P.boundaryLayer && !S->have_sponge) { set_error("boundaryLayer needs cudns_set_sponge first"); return CUDNS_ESTATE; }
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
     CK(cudaSetDevice(S->P.device));
     if (nsteps == 0) return CUDNS_OK;
-    if (S->hist_cap < nsteps) {
+    if (S->hist_cap < nsteps) {                       // grows in steps of 4096 entries: no cudaFree/cudaMalloc between calls of similar length
+        const int cap = (nsteps + 4095) / 4096 * 4096;
         cudaFree(S->d_hist); S->d_hist = nullptr;
-        CK(cudaMalloc((void **)&S->d_hist, 3 * (size_t)nsteps * sizeof(double)));
-        S->hist_cap = nsteps;
+        CK(cudaMalloc((void **)&S->d_hist, 3 * (size_t)cap * sizeof(double)));
+        S->hist_cap = cap;
     }
-    CK(cudaMemsetAsync(S->d_hist, 0xff, 3 * (size_t)S->hist_cap * sizeof(double), S->st));   // NaN = "not written"
+    for (int a = 0; a < 3; a++) CK(cudaMemsetAsync(S->d_hist + (size_t)a * S->hist_cap, 0xff, (size_t)nsteps * sizeof(double), S->st));   // NaN = "not written"
     double *h_time = S->d_hist, *h_p1 = S->d_hist + S->hist_cap, *h_p2 = S->d_hist + 2 * S->hist_cap;
     double *sc = S->d_scal;
     const cudns_params &P = S->P;
@@ -663,7 +735,7 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
                 launch_dt_combine(sc + SC_DT, sc + SC_RED0, sc + SC_STALE1, P.CFL, S->st); S->launches++;
             }
             if (P.forcing) {
-                launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->st);
+                launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->d_bulk, S->st);
                 reduce_across(S, sc + SC_BULK0, 4, 1);
                 launch_scalar_ops(2, sc + SC_DPDZ, sc + SC_BULK0, nullptr, S->st);
                 S->launches += 2;
@@ -674,7 +746,7 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
         S->launches += 2;
         CK(cudaMemcpyAsync(h_time + istep, sc + SC_TIME, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
         if (istep % P.checkBulk == 0) {                                       // calcBulk, calc_stress.cu:162-201
-            launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->st); S->launches++;
+            launch_bulk_reduce(S->kc, S->state[S->cur], sc + SC_BULK0, S->d_bulk, S->st); S->launches++;
             reduce_across(S, sc + SC_BULK0, 4, 1);
             if (P.forcing) {
                 launch_scalar_ops(3, h_p1 + istep, sc + SC_BULK0, nullptr, S->st); S->launches++;
@@ -719,6 +791,8 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
     CK(cudaStreamSynchronize(S->st));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error(std::string("advance: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
+    { int rc0 = check_halo_error(S); if (rc0) return rc0; }
+    stage_timer_collect(S);
     if (par1 || par2) {
         std::vector<double> b1(nsteps), b2(nsteps);
         CK(cudaMemcpy(b1.data(), h_p1, nsteps * sizeof(double), cudaMemcpyDeviceToHost));
@@ -728,6 +802,28 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
             if (par2 && i % P.checkBulk == 0 && P.forcing) par2[i] = b2[i];
         }
     }
+    return CUDNS_OK;
+}
+
+// switch the per-stage event timing of cudns_advance on (resetting the sums) or off; read the sums of the calls made since
+int cudns_set_stage_timing(cudns_handle S, int on) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    if (!S->tm) S->tm = new StageTimer();
+    StageTimer *tm = S->tm;
+    if (on && tm->ev.empty()) {
+        tm->ev.resize(4 * 1024);
+        for (auto &e : tm->ev) CK(cudaEventCreate(&e));
+    }
+    tm->on = on != 0; tm->used = 0;
+    if (on) { tm->theta_ms = tm->stage_ms = tm->halo_ms = 0; tm->n = 0; }
+    return CUDNS_OK;
+}
+int cudns_get_stage_timing(cudns_handle S, double *theta_ms, double *stage_ms, double *halo_ms, uint64_t *nstages) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    const StageTimer *tm = S->tm;
+    if (theta_ms) *theta_ms = tm ? tm->theta_ms : 0; if (stage_ms) *stage_ms = tm ? tm->stage_ms : 0;
+    if (halo_ms) *halo_ms = tm ? tm->halo_ms : 0; if (nstages) *nstages = tm ? tm->n : 0;
     return CUDNS_OK;
 }
 
@@ -744,7 +840,7 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(e0, S->st));
         StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
-        p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr; p.viscmax = nullptr;
+        p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr;
         const bool fast = stage_is_fast(S, p, c);
         if (fast) {
             p.theta = S->state[a] + 7 * S->L.vol;
@@ -927,7 +1023,8 @@ int cudns_calc_profiles(cudns_handle S, double *prof) {
     if (!S || !prof) { set_error("NULL argument"); return CUDNS_EINVAL; }
     if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
     CK(cudaSetDevice(S->P.device));
-    int rc = prof_scratch(S); if (rc) return rc;
+    int rc = need_allreduce(S); if (rc) return rc;
+    rc = prof_scratch(S); if (rc) return rc;
     const int mx = S->L.mx;
     double *partial = S->d_prof, *mean = partial + profile_partial_doubles(S->kc), *var = mean + 5 * mx;
     const double scale = 1.0 / ((double)S->P.my * (double)S->P.mz);        // global row count: slabs add up to the whole plane
@@ -950,7 +1047,8 @@ int cudns_calc_retau(cudns_handle S, double *retau) {
     if (!S || !retau) { set_error("NULL argument"); return CUDNS_EINVAL; }
     if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
     CK(cudaSetDevice(S->P.device));
-    int rc = prof_scratch(S); if (rc) return rc;
+    int rc = need_allreduce(S); if (rc) return rc;
+    rc = prof_scratch(S); if (rc) return rc;
     double *partial = S->d_prof, *out = partial + profile_partial_doubles(S->kc) + 10 * (size_t)S->L.mx;
     launch_retau(S->kc, S->state[S->cur], partial, out, 1.0 / ((double)S->P.my * (double)S->P.mz), S->st);
     reduce_across(S, out, 1, 1);

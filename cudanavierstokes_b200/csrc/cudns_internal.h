@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/cudns.h"
@@ -34,10 +35,9 @@ struct KConst {
     double aF[MAXS + 1];         // advective first-derivative weights a_l, l=1..s ( = -coeffF[s-l], globals.h:69-82)
     double aV[MAXS + 1];         // viscous   first-derivative weights
     double bV[MAXS + 1];         // viscous second-derivative weights b_0..b_v ( = coeffVS[v-l] )
-    // the same weights pre-scaled by the grid spacing of direction d (stage kernel): cC = -a_l/(4 dx_d) (split-form
-    // flux sums), cP = a_l/dx_d (pressure gradient, advective order), c1 = a_l/dx_d and c2 = b_l/dx_d^2 (viscous order)
-    double cC[3][MAXS + 1], cP[3][MAXS + 1], c1[3][MAXS + 1], c2[3][MAXS + 1];
-    // lean stage kernel: cf[d][l] = { -a_l/(4 dx_d), -a_l/dx_d (advective order), a_l/dx_d, b_l/dx_d^2 (viscous order) },
+    // the same weights pre-scaled by the grid spacing of direction d: c1 = a_l/dx_d (viscous order; dilatation pass)
+    double c1[3][MAXS + 1];
+    // stage kernels: cf[d][l] = { -a_l/(4 dx_d), -a_l/dx_d (advective order), a_l/dx_d, b_l/dx_d^2 (viscous order) },
     // c1t = a_l/(3 dx_d) (viscous order), c20sum = sum_d b_0/dx_d^2
     double cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
     double cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
@@ -75,7 +75,6 @@ struct StagePtrs {
                                  // or qout itself for the periodic wrap on one device); the stage kernel stores its first / last
                                  // gz planes straight into the neighbour's ghost planes.  nullptr: no such neighbour / not connected
     double *rhs_out;             // test path: write K only (5 unpadded) and skip the update
-    double *viscmax;             // optional: atomic max of mu-based dt limiter (stale-mu semantics)
 };
 
 // TMA descriptors of one state buffer (+ theta) for the stage kernel: the tile with its x/y stencil halos
@@ -122,7 +121,9 @@ void launch_pad(const KConst &kc, const double *src5[5], double *q5, cudaStream_
 void launch_unpad(const KConst &kc, const double *q5, double *dst5[5], cudaStream_t st);
 // reductions: out[0] = max_p conv limiter, out[1] = max_p visc limiter (uses fresh mu), out[2..] sums
 void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st);
-void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st);
+// scratch: bulk_scratch_doubles() doubles owned by the calling solver (block partials, then the completion counter; zeroed once)
+void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, double *scratch, cudaStream_t st);
+int bulk_scratch_doubles();
 void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
 // wall-normal profiles / friction Reynolds number (calcAvgChan, printRes): see kernels.cu
 void launch_profile_partial(const KConst &kc, const double *q, const double *mean, double *partial, int pass, cudaStream_t st);
@@ -132,7 +133,23 @@ int profile_partial_doubles(const KConst &kc);
 void launch_retau(const KConst &kc, const double *q, double *partial, double *out, double scale, cudaStream_t st);
 // cross-GPU stage hand-shake over peer memory: store `epoch` into the two neighbours' mailbox slots / spin until both own slots reach it
 void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st);
-void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, cudaStream_t st);
+// the wait gives up after timeout_ns (device global timer) and stores `epoch` into *err_word (0 = never timed out): a neighbour that
+// died or runs a different number of stages must not hang the device for good
+void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, unsigned long long timeout_ns,
+                      unsigned long long *err_word, cudaStream_t st);
+
+// opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair and several
+// devices may be driven from one process (cudns_peer_info.local_ptr), so it is remembered per device, under a lock
+template <auto Kernel>
+inline void opt_in_smem(int bytes) {
+    static std::mutex m;
+    static unsigned long long done = 0;                  // bit d: set on device d
+    int dev = 0; cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(m);
+    if (dev < 64 && ((done >> dev) & 1ull)) return;
+    cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (dev < 64) done |= 1ull << dev;
+}
 
 bool rhs_stage_supported(int s, int v);
 

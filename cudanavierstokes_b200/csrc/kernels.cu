@@ -311,17 +311,10 @@ __global__ void __launch_bounds__(256) bulk_reduce_kernel(KConst c, const double
         if (threadIdx.x == 0) *counter = 0;
     }
 }
-static double *g_bulk_partial[16] = {nullptr};
-static unsigned int *g_bulk_counter[16] = {nullptr};
-void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, cudaStream_t st) {
-    int dev = 0; cudaGetDevice(&dev);
-    const int nb = 148 * 4;
-    if (!g_bulk_partial[dev]) {
-        cudaMalloc(&g_bulk_partial[dev], 4 * nb * sizeof(double));
-        cudaMalloc(&g_bulk_counter[dev], sizeof(unsigned int));
-        cudaMemset(g_bulk_counter[dev], 0, sizeof(unsigned int));
-    }
-    bulk_reduce_kernel<<<nb, 256, 0, st>>>(kc, q, out4, g_bulk_partial[dev], g_bulk_counter[dev]);
+constexpr int BULK_NB = 148 * 4;
+int bulk_scratch_doubles() { return 4 * BULK_NB + 1; }
+void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, double *scratch, cudaStream_t st) {
+    bulk_reduce_kernel<<<BULK_NB, 256, 0, st>>>(kc, q, out4, scratch, (unsigned int *)(scratch + 4 * BULK_NB));
 }
 
 // tiny scalar kernels (deviceSumOne, deviceAdvanceTime, deviceCalcPress, ... cuda_math.cu:17-52, calc_stress.cu:12-18)
@@ -353,14 +346,20 @@ __global__ void halo_signal_kernel(unsigned long long *lo_slot, unsigned long lo
     if (lo_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(lo_slot), "l"(epoch) : "memory");
     if (hi_slot) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hi_slot), "l"(epoch) : "memory");
 }
-__global__ void halo_wait_kernel(const unsigned long long *slots, int need_lo, int need_hi, unsigned long long epoch) {
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__global__ void halo_wait_kernel(const unsigned long long *slots, int need_lo, int need_hi, unsigned long long epoch,
+                                 unsigned long long timeout_ns, unsigned long long *err_word) {
     // slots[0]: written by the lower neighbour, slots[1]: by the upper one
+    const unsigned long long t0 = global_ns();
     for (int n = 0; n < 2; n++) {
         if (!(n == 0 ? need_lo : need_hi)) continue;
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(slots + n) : "memory");
-            if (v < epoch) __nanosleep(200);
+            if (v < epoch) {
+                __nanosleep(200);
+                if (global_ns() - t0 > timeout_ns) { if (*err_word == 0) *err_word = epoch; return; }    // reported by cudns_advance
+            }
         } while (v < epoch);
     }
     __threadfence_system();
@@ -368,8 +367,9 @@ __global__ void halo_wait_kernel(const unsigned long long *slots, int need_lo, i
 void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st) {
     halo_signal_kernel<<<1, 1, 0, st>>>(peer_lo_slot, peer_hi_slot, epoch);
 }
-void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, cudaStream_t st) {
-    halo_wait_kernel<<<1, 1, 0, st>>>(my_slots, need_lo, need_hi, epoch);
+void launch_halo_wait(const unsigned long long *my_slots, int need_lo, int need_hi, unsigned long long epoch, unsigned long long timeout_ns,
+                      unsigned long long *err_word, cudaStream_t st) {
+    halo_wait_kernel<<<1, 1, 0, st>>>(my_slots, need_lo, need_hi, epoch, timeout_ns, err_word);
 }
 
 }  // namespace cudns

@@ -305,9 +305,11 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     if (tid == 0) issue_bundle(kbeg, 0);
 
     // ring slot of plane k-S+n: column offset ring_off[s0 + n] with s0 = (k-S) mod R
-    int s0 = (kbeg - S + 16 * R) % R;
+    // (recomputed from k every plane: as a loop-carried counter it was spilled, and the reload -- an L2 round trip -- stalled the
+    // loop branch for 3.7 % of the kernel time, profiles/r01_stage_fast8_512_ncu_full.txt)
     const size_t N = (size_t)L.mx * L.my * L.mz;
-    for (int k = kbeg; k < kend_now(); k++, s0 = (s0 + 1 == R) ? 0 : s0 + 1) {
+    for (int k = kbeg; k < kend_now(); k++) {
+        const int s0 = (int)((unsigned)(k - S + 16 * R) % (unsigned)R);
         // everything that depends on the thread index is rebuilt here and again before the update instead of being kept in (or
         // spilled from) registers across the stencil sums
         const int tn = tid_now();
@@ -513,13 +515,9 @@ __global__ void __launch_bounds__(256) derive_aux_kernel(const __grid_constant__
 template <int S, int V, int TY>
 static void launch_t(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, cudaStream_t st) {
     using G = FCfg<S, TY>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(stage_kernel<S, V, TY, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
-        cudaFuncSetAttribute(stage_kernel<S, V, TY, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
-        cudaFuncSetAttribute(stage_kernel<S, V, TY, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::bytes);
-        attr_set = true;
-    }
+    opt_in_smem<stage_kernel<S, V, TY, 0>>((int)G::bytes);
+    opt_in_smem<stage_kernel<S, V, TY, 1>>((int)G::bytes);
+    opt_in_smem<stage_kernel<S, V, TY, 2>>((int)G::bytes);
     const int gx = (kc.L.mx + TX - 1) / TX, gy = (kc.L.my + TY - 1) / TY;
     // z chunks: every chunk pays a 2S-plane prologue, so keep them >= 32 planes; more chunks smooth the tail over the SMs
     const int cols = gx * gy, resident = 148 * (TY == 16 ? 1 : 2);

@@ -200,12 +200,8 @@ void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaSt
 #define CUDNS_THETA_CASE(VV)                                                                        \
     {                                                                                               \
         const size_t sm = (size_t)NST * (TYT * UX + (TYT + 2 * VV) * TXT + NTT) * sizeof(double);   \
-        static bool attr = false;                                                                   \
-        if (!attr) {                                                                                \
-            cudaFuncSetAttribute(theta_march_kernel<VV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   \
-            cudaFuncSetAttribute(theta_march_kernel<VV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);  \
-            attr = true;                                                                            \
-        }                                                                                           \
+        opt_in_smem<theta_march_kernel<VV, true>>((int)sm);                                         \
+        opt_in_smem<theta_march_kernel<VV, false>>((int)sm);                                        \
         if (gen) theta_march_kernel<VV, true><<<grid, NTT, sm, st>>>(kc, q, theta, zchunk);         \
         else theta_march_kernel<VV, false><<<grid, NTT, sm, st>>>(kc, q, theta, zchunk);            \
     }

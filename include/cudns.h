@@ -183,6 +183,13 @@ int cudns_get_stream(cudns_handle h, void **stream);
 int cudns_get_counters(cudns_handle h, uint64_t *kernel_launches, uint64_t *rk_stages);
 /* per-kernel device time of the last cudns_profile_stage() call, in ms: theta, rhs_stage, halo */
 int cudns_profile_stage(cudns_handle h, int reps, float *ms_theta, float *ms_rhs, float *ms_halo);
+/* per-kernel device times of the step loop itself (no reference counterpart: the reference only prints whole-run wall time,
+ * main.cpp:80-96): cudns_set_stage_timing(h, 1) resets the sums and makes every later cudns_advance bracket the dilatation pass,
+ * the stage kernel and the hand-shake of each stage with CUDA events (up to 1024 stages per call); cudns_get_stage_timing returns
+ * the summed milliseconds and the number of stages they cover -- the kernel time under sustained load, next to the isolated-launch
+ * time of cudns_profile_stage */
+int cudns_set_stage_timing(cudns_handle h, int on);
+int cudns_get_stage_timing(cudns_handle h, double *theta_ms, double *stage_ms, double *halo_ms, uint64_t *nstages);
 
 /* ---- output and restart that do not stall the step loop ------------------------------------------
  * writeField (init.cpp:23-30) -> saveFileMPI (comm.cpp:205-250): fields/{r,u,v,w,e}.<%07d>.bin of the GLOBAL grid, raw float64

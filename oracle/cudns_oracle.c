@@ -192,6 +192,10 @@ ora_solver *ora_create(const ora_params *p) {
     return S;
 }
 
+/* host threads of the OpenMP regions (bench.py's CPU baseline: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers) */
+void ora_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int ora_get_threads(void) { return omp_get_max_threads(); }
+
 void ora_destroy(ora_solver *S) {
     if (!S) return;
     free(S->x); free(S->xp); free(S->xpp); free(S->dxv); free(S->y); free(S->z); free(S->coeffVSx);

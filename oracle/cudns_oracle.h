@@ -68,6 +68,9 @@ void ora_params_blayer(ora_params *p);
  * setGPUParameters (cuda_utils.cu:49-139). */
 ora_solver *ora_create(const ora_params *p);
 void ora_destroy(ora_solver *s);
+/* host threads used by the OpenMP loops (CPU-baseline timing) */
+void ora_set_threads(int n);
+int ora_get_threads(void);
 
 /* grid + metrics access (length mx / my / mz) */
 const double *ora_x(const ora_solver *s);

@@ -55,6 +55,8 @@ def lib():
         L.ora_params_blayer.argtypes = [P]
         L.ora_create.argtypes = [P]; L.ora_create.restype = C.c_void_p
         L.ora_destroy.argtypes = [C.c_void_p]
+        L.ora_set_threads.argtypes = [C.c_int]
+        L.ora_get_threads.restype = C.c_int
         for name in ("ora_x", "ora_xp", "ora_xpp", "ora_y", "ora_z", "ora_dxv", "ora_coeffVSx",
                      "ora_r", "ora_u", "ora_v", "ora_w", "ora_e", "ora_spongeX", "ora_spongeZ"):
             f = getattr(L, name); f.argtypes = [C.c_void_p]; f.restype = dp
@@ -84,6 +86,14 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def set_threads(n=None):
+    """use n host threads (default: every core this process may run on) whatever OMP_NUM_THREADS says; returns the count in effect"""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().ora_set_threads(int(n))
+    return int(lib().ora_get_threads())
 
 
 def params_tgv(n, stencil, **over):

@@ -24,8 +24,9 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": (ndoubles,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def _run_two_ranks(p_of, full, grid, steps, peer):
-    """advance the same problem as 2 slabs in two threads; returns the gathered state"""
+def _run_two_ranks(p_of, full, grid, steps, peer, sponge=None, scalars=None):
+    """advance the same problem as 2 slabs in two threads; returns the gathered state.  sponge = (sigma_x, sigma_z, ref5) GLOBAL
+    tables (each rank takes its slab); scalars: optional list that receives rank 0's dt / dpdz / time after the run"""
     import torch
     nr = 2
     sols = [cd.Solver(p_of(nr, r), grid) for r in range(nr)]
@@ -70,9 +71,14 @@ def _run_two_ranks(p_of, full, grid, steps, peer):
                 sols[r].halo_connect(infos[(r - 1) % nr], infos[(r + 1) % nr])
             bar.wait()
             mzl = sols[r].mzl
+            if sponge is not None:
+                sx, sz, ref = sponge
+                sols[r].set_sponge(sx, sz[r * mzl:(r + 1) * mzl], ref[:, r * mzl:(r + 1) * mzl])
             sols[r].set_state([a[r * mzl:(r + 1) * mzl] for a in full])
             sols[r].advance(steps)
             out[r] = sols[r].get_state()
+            if scalars is not None and r == 0:
+                scalars.append(sols[r].scalars())
         except Exception as e:       # noqa: BLE001
             errors.append(e); bar.abort()
 
@@ -107,6 +113,59 @@ def test_two_slabs_equal_one(case, peer):
     multi = _run_two_ranks(p_of, full, grid, 12, peer)
     errs = [relerr(a, b) for a, b in zip(conserved(multi), conserved(single))]
     assert max(errs) < 1e-13, errs          # multi-GPU == single-GPU to 1e-13 (observed: identical)
+
+
+def _golden_params(name):
+    import oracle_binding as ob
+    from common import CONFIGS, apply_cfg
+    cfg = CONFIGS[name]
+    op = apply_cfg(ob.params_tgv(24, 3), cfg)
+
+    def p_of(nranks, rank):
+        cp = apply_cfg(cd.Params(), cfg); cp.gam = 1.4; cp.TwallTop = cp.TwallBot = 1.0; cp.quirk_q1 = 1
+        for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
+                  "kC", "LP", "amp1", "amp2", "omega2"):
+            setattr(cp, k, getattr(op, k))
+        cp.nranks = nranks; cp.rank = rank; cp.device = 0
+        return cp
+    return cfg, p_of
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("peer", [True, False])
+def test_two_slabs_channel_forcing(peer):
+    """isothermal-wall channel with the pressure-gradient controller: the bulk integrals (calcPressureGrad calc_stress.cu:98-120) are
+    cross-rank SUMs, dt a cross-rank MAX; walls in x, stretched grid, periodic z across the slab seam"""
+    cfg, p_of = _golden_params("chan_s3v2")
+    p1 = p_of(1, 0)
+    grid = cd.init_grid(p1)
+    full = cd.init_channel(p1, grid)
+    ref = cd.Solver(p1, grid); ref.set_state(full); ref.advance(12); single = ref.get_state(); sc1 = ref.scalars(); ref.close()
+    sc2 = []
+    multi = _run_two_ranks(p_of, full, grid, 12, peer, scalars=sc2)
+    errs = [relerr(a, b) for a, b in zip(conserved(multi), conserved(single))]
+    # the forcing integrals are summed per slab and then across ranks: a different order than one device's single sum, so dpdz (and
+    # with it the state) agrees to round-off, not bit for bit
+    assert max(errs) < 1e-12, errs
+    assert abs(sc2[0]["dpdz"] - sc1["dpdz"]) <= 1e-12 * abs(sc1["dpdz"])
+    assert abs(sc2[0]["dt"] - sc1["dt"]) <= 1e-14 * sc1["dt"]
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("peer", [True, False])
+def test_two_slabs_boundary_layer(peer):
+    """spatially developing boundary layer: z is NOT periodic (the global bottom / top slabs have no neighbour there and rebuild the
+    extrapolation ghosts on chip, api.cu ghost_targets / handshake), sponges and wall blowing/suction indexed by the GLOBAL plane"""
+    from common import blasius_profiles
+    cfg, p_of = _golden_params("bl_s3v2")
+    p1 = p_of(1, 0)
+    grid = cd.init_grid(p1)
+    x, r, u, w, e = blasius_profiles()
+    sx, sz, refq, ic = cd.build_sponge(p1, grid, x[1:], r[1:], u[1:], w[1:])
+    ref = cd.Solver(p1, grid); ref.set_sponge(sx, sz, refq); ref.set_state(ic); ref.advance(12); single = ref.get_state(); ref.close()
+    multi = _run_two_ranks(p_of, ic, grid, 12, peer, sponge=(sx, sz, refq))
+    errs = [relerr(a, b, floor=1e-30) for a, b in zip(conserved(multi), conserved(single))]
+    assert max(errs) < 1e-13, errs
 
 
 @pytest.mark.timeout(600)

@@ -47,6 +47,23 @@ def test_oracle_matches_reference_gpu_binary(name):
     assert abs(p1[0] - g["solution"][0, 2]) < 1e-6
 
 
+def test_survey_appendix_c_anchors_c1_64():
+    """C1 as BASELINE.md section 6 writes it (64^3, s=v=3, low-storage RK3, 100 steps): par1 history, dt at the step-90 refresh and
+    samples of the final state from the surveyor's independent numpy restatement (SURVEY.md Appendix C, quirk Q1 on)"""
+    o = ob.Oracle(ob.params_tgv(64, 3)); o.init_chit()
+    t, p1, _ = o.run(100)
+    for i, v in {0: 2.500000000000000e-01, 10: 2.499583342263006e-01, 20: 2.499169187474198e-01, 50: 2.497906456827162e-01,
+                 90: 2.496226872797876e-01}.items():
+        assert abs(p1[i] - v) < 1e-13, i
+    assert abs(o.dt - 4.467409949993332e-03) < 1e-14
+    assert abs(o.bulk()[0] - 2.495801472523635e-01) < 1e-13
+    st = o.state()
+    assert abs(st[0].sum() - 64 ** 3) < 1e-7
+    assert abs(np.abs(st[3]).max() - 1.110551585542883e-01) < 1e-13
+    assert abs(st[0][0, 0, 0] - 1.005253830519991e+00) < 1e-13 and abs(st[4][3, 5, 7] - 1.790226096680589e+02) < 1e-10
+    assert abs(st[4].mean() - 1.786964632771293e+02) < 1e-10
+
+
 def test_survey_appendix_c_anchors_32():
     """32^3, s=v=3, 20 steps: dt0, dt10 and par1 from the surveyor's independent numpy restatement"""
     o = ob.Oracle(ob.params_tgv(32, 3)); o.init_chit()

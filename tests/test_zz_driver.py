@@ -49,7 +49,6 @@ def test_config_file_and_errors(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="driver + on-device diagnostics not yet seen on hardware (round-1 GPU budget exhausted)")
 def test_driver_reproduces_the_reference_channel_run(tmp_path):
     name = "chan_s3v2"
     cfg = CONFIGS[name]; g = load_golden(name)
@@ -72,3 +71,9 @@ def test_driver_reproduces_the_reference_channel_run(tmp_path):
     assert np.allclose(sol[:, 1:], g["solution"][:, 1:], rtol=0, atol=2e-6)          # "%lf": six decimals on both sides
     prof = np.loadtxt(out / "prof.txt")
     assert prof.shape == (cfg["mx"], 11) and np.isfinite(prof).all()
+    # prof.txt = calcAvgChan (init.cpp:150-208) of the last file, "%lf": x, Reynolds mean of rho, Favre means of u,v,w, mean of rho E, variances
+    r_, u_, v_, w_, e_ = g["file2"]
+    rm = r_.mean(axis=(0, 1)); fav = [(r_ * q).mean(axis=(0, 1)) / rm for q in (u_, v_, w_)]; em = e_.mean(axis=(0, 1))
+    want = [g["x"], rm] + fav + [em, ((r_ - rm) ** 2).mean(axis=(0, 1))] + [((q - m) ** 2).mean(axis=(0, 1)) for q, m in zip((u_, v_, w_), fav)] + \
+           [((e_ - em) ** 2).mean(axis=(0, 1))]
+    assert np.allclose(prof, np.stack(want, axis=1), rtol=0, atol=2e-6)
