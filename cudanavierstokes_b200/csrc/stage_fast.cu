@@ -25,6 +25,7 @@
 #define LEAN_TY8 CUDNS_LEAN_TY_LINEAR
 #define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
 #include "stage_lean.inc"
+#include "stage_point.h"
 
 #ifndef FAST_L2_HINTS
 #define FAST_L2_HINTS 0       // 1: L2 eviction hints on the TMA loads + streaming stores (measured: no gain, 143 vs 149 B/pt read)
@@ -38,7 +39,6 @@ namespace fast {
 
 using namespace lean;
 
-enum { FR = 0, FU, FV, FW, FH, FT, FD, NF };   // ring / shared-plane quantities
 
 template <int S, int TY_> struct FCfg {
     static constexpr int TY = TY_;                              // tile rows = warps per CTA: 16 (one CTA per SM) or 8 (two)
@@ -67,15 +67,6 @@ template <int S, int TY_> struct FCfg {
     static_assert(bytes <= (TY == 16 ? 227 : 112) * 1024, "shared memory budget");
     static_assert((CSZ * 8) % 128 == 0 && (NT * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
-
-// H and T of a stored point: calcState (cuda_main.cu:218-242) restricted to what the kernels stage.  ONE definition for the update
-// of the stage kernel and for derive_aux_kernel (same operation order -> same bits as eos_q / eos7 of the older kernels)
-__device__ __forceinline__ void eos_ht(const KConst &c, double r, double rinv, double u, double v, double w, double e, double &H, double &T) {
-    const double en = fma(e, rinv, -0.5 * fma(u, u, fma(v, v, w * w)));
-    const double t = c.cvInv * en;
-    const double p = r * c.Rgas * t;
-    H = (e + p) * rinv; T = t;
-}
 
 // TMA loads with an L2 eviction hint.  The stage streams ~250 B per point through L2 but re-reads only the tile interior it
 // loaded S planes ahead for the ring (as part of the halo'd plane): that window survives in L2 only if everything else -- the
@@ -160,41 +151,6 @@ __device__ __forceinline__ void st_out(double *p, double v) {
 #endif
 }
 
-// running sums of one point
-struct Acc {
-    double r[5];               // convective sums; the momentum entries also collect -dp/dx_d
-    double lapu[3], lapT;      // sum_d D2_d u_m + (1/3) d theta / d x_m ; sum_d D2_d T
-    double g[3][3];            // g[d][m] = d u_m / d x_d
-    double dT[3];
-};
-
-// both neighbours of direction D at offset l: split-form convective sums in telescoped pair form, pressure gradient from rho*T,
-// viscous-order first and second differences (dir_sums of stage_lean.inc with PRT)
-template <int D, int V>
-__device__ __forceinline__ void pair_step(const KConst &c, const int l, const double (&C)[NF], const double (&Pn)[NF], const double (&Mn)[NF], Acc &A,
-                                          double &aM) {
-    const double cC = c.cf[D][l][0];
-    const double cu = cC * C[FU + D];
-    const double Ap = (C[FR] + Pn[FR]) * fma(cC, Pn[FU + D], cu);
-    const double Am = (C[FR] + Mn[FR]) * fma(cC, Mn[FU + D], cu);
-    aM += Ap - Am;
-    A.r[1] = fma(Ap, Pn[FU], A.r[1]); A.r[1] = fma(-Am, Mn[FU], A.r[1]);
-    A.r[2] = fma(Ap, Pn[FV], A.r[2]); A.r[2] = fma(-Am, Mn[FV], A.r[2]);
-    A.r[3] = fma(Ap, Pn[FW], A.r[3]); A.r[3] = fma(-Am, Mn[FW], A.r[3]);
-    A.r[4] = fma(Ap, Pn[FH], A.r[4]); A.r[4] = fma(-Am, Mn[FH], A.r[4]);
-    A.r[1 + D] = fma(c.cfp[D][l], fma(Pn[FR], Pn[FT], -(Mn[FR] * Mn[FT])), A.r[1 + D]);
-    if (l <= V) {
-        const double k1 = c.cf[D][l][2], k2 = c.cf[D][l][3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-            A.g[D][m] = fma(k1, Pn[FU + m] - Mn[FU + m], A.g[D][m]);
-            A.lapu[m] = fma(k2, Pn[FU + m] + Mn[FU + m], A.lapu[m]);
-        }
-        A.dT[D] = fma(k1, Pn[FT] - Mn[FT], A.dT[D]);
-        A.lapT = fma(k2, Pn[FT] + Mn[FT], A.lapT);
-        A.lapu[D] = fma(c.c1t[D][l], Pn[FD] - Mn[FD], A.lapu[D]);
-    }
-}
 // one neighbour of direction D at offset +l (PLUS) or -l: the same sums, one side at a time (one more FP64 instruction per pair,
 // half the registers for neighbour values)
 template <int D, int V, bool PLUS>
@@ -219,12 +175,6 @@ __device__ __forceinline__ void side_step(const KConst &c, const int l, const do
         A.lapu[D] = fma(PLUS ? c.c1t[D][l] : -c.c1t[D][l], Nq[FD], A.lapu[D]);
     }
 }
-// the direction is complete: central values times its mass-flux sum
-__device__ __forceinline__ void close_dir(const double (&C)[NF], Acc &A, const double aM) {
-    A.r[0] = fma(2.0, aM, A.r[0]);
-    A.r[1] = fma(C[FU], aM, A.r[1]); A.r[2] = fma(C[FV], aM, A.r[2]); A.r[3] = fma(C[FW], aM, A.r[3]); A.r[4] = fma(C[FH], aM, A.r[4]);
-}
-
 // MODE 0: write the right-hand side only (test path); 1: Runge-Kutta update without an RA operand; 2: with RA
 template <int S, int V, int TY, int MODE>
 __global__ void __launch_bounds__(TX * TY, TY == 16 ? 1 : 2)

@@ -9,7 +9,7 @@ import pytest
 
 import cudanavierstokes_b200 as cd
 import oracle_binding as ob
-from common import conserved, make_pair, relerr
+from common import cons_errs, conserved, make_pair, relerr
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -21,7 +21,7 @@ def test_c1_tgv64_rk3_6th_order_1_10_100_steps():
         o, s, grid = make_pair(op)
         o.init_chit(); s.set_state(o.state())
         t0, a1, _ = o.run(n); t1, b1, _ = s.advance(n)
-        errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+        errs = cons_errs(s.get_state(), o.state())
         assert max(errs) < TOL, (n, errs)
         assert abs(s.scalars()["dt"] - o.dt) <= 1e-13 * o.dt, n
         np.testing.assert_allclose(t1, t0, rtol=0, atol=1e-12)
@@ -55,7 +55,7 @@ def test_tgv128_8th_order_steps_vs_oracle(scheme):
     a = s.rhs(); b = o.rhs()
     assert max(relerr(x, y) for x, y in zip(a, b)) < 1e-11
     o.run(3); s.advance(3)
-    errs = [relerr(x, y) for x, y in zip(conserved(s.get_state()), conserved(o.state()))]
+    errs = cons_errs(s.get_state(), o.state())
     assert max(errs) < TOL, errs
 
 
