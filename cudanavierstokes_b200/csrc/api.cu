@@ -110,6 +110,8 @@ struct cudns_solver {
     FastMaps fmaps[3];           // its TMA descriptors per state buffer (opa is patched per launch)
     CUtensorMap frmap[2];        // R1 / R2 with its tile
     bool aux_valid[3];           // H, T of state[b] (ghosts included) match its (rho,u,v,w,rho*E)
+    bool duo;                    // the fifth-generation kernel (stage_duo.inc) serves EVERY stage of this configuration (CUDNS_DUO=0: off)
+    DuoMaps dmaps[3];            // its TMA descriptors per state buffer
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcudns does not link libcuda)
@@ -194,6 +196,14 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         S->fast = p->viscexp == 1.0 && p->periodicX && !p->nonUniformX && !p->boundaryLayer && !(we && (std::string(we) == "0" || std::string(we) == "1")) &&
                   (size_t)fast_smem_bytes(s, S->fast_ty) <= prop.sharedMemPerBlockOptin;
         S->nfb = S->fast ? FAST_NFB : 5;
+        // fifth generation: two x-adjacent points per thread, every Runge-Kutta stage shape; needs an even mx (16-byte rows)
+        // It serves Kutta RK3 and RK4 by default (the fourth generation cannot: those stages fell back to the lean kernel); for
+        // low-storage RK3 the fourth generation is still ~5 % faster (2 x 8 warps per SM hide more latency than 8 warps with two
+        // points each): CUDNS_DUO=1 forces the fifth generation there too, CUDNS_DUO=0 switches it off
+        const char *de = getenv("CUDNS_DUO");
+        const bool ls3 = p->lowStorage && !p->rk4;
+        const bool want = de ? std::string(de) != "0" : !ls3;
+        S->duo = S->fast && !fe && mx % 2 == 0 && want && (size_t)duo_smem_bytes(s) <= prop.sharedMemPerBlockOptin;
     }
     S->block_doubles = (size_t)S->nstate * S->nfb * L.vol;
     S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
@@ -308,6 +318,16 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
                 }
             }
             if ((rc = make_rmap(&S->frmap[0], L, S->R1, fty)) || (S->R2 && (rc = make_rmap(&S->frmap[1], L, S->R2, fty)))) { cudns_destroy(S); return rc; }
+        }
+        if (S->duo) {
+            const int DXb = DUO_TX + 2 * GX, DYb = DUO_TY + 2 * s;
+            for (int b = 0; b < S->nstate; b++) {
+                double *q = S->state[b];
+                if ((rc = make_map(&S->dmaps[b].q4box, L, q, 4, DXb, DYb)) || (rc = make_map(&S->dmaps[b].a3box, L, q + 5 * L.vol, 3, DXb, DYb)) ||
+                    (rc = make_map(&S->dmaps[b].q4int, L, q, 4, DUO_TX, DUO_TY)) || (rc = make_map(&S->dmaps[b].a3int, L, q + 5 * L.vol, 3, DUO_TX, DUO_TY))) {
+                    cudns_destroy(S); return rc;
+                }
+            }
         }
         if (S->wide) {
             const int wty = CUDNS_LEAN_TY_WIDE, WYb = wty + 2 * s;
@@ -546,6 +566,13 @@ int cudns_get_scalars(cudns_handle S, double *dt, double *dpdz, double *time) {
 
 // the stage kernel of the selected generation; p.qin = state[in], p.qbase = state[base]
 static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoef &c, int in, int base) {
+    if (S->duo && !(p.RB && p.RW && c.wOld != 0.0)) {        // (RB and an accumulated RW share one stash slot: never both in our schemes)
+        // 8-field buffers: theta of the input state is its field 7 (run_stage put it there), H and T are rebuilt first when the
+        // buffer was not written by a kernel that stores them
+        if (!S->aux_valid[in]) { launch_derive_aux(S->kc, S->state[in], S->st); S->launches++; S->aux_valid[in] = true; }
+        launch_rhs_stage_duo(S->kc, p, c, S->dmaps[in], S->st);
+        return;
+    }
     {
         // the wide variant stages one operand tile only (RA): every low-storage RK3 stage and the test path qualify
         const bool wide = S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
@@ -572,7 +599,7 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
 
 // will launch_stage_any serve this stage with the fast kernel?
 static bool stage_is_fast(const cudns_solver *S, const StagePtrs &p, const StageCoef &c) {
-    return S->fast && S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin;
+    return (S->duo && !(p.RB && p.RW && c.wOld != 0.0)) || (S->fast && S->wide && !p.RB && !(p.RW && c.wOld != 0.0) && p.qbase == p.qin);
 }
 
 // does this solver's stage kernel write the z ghost planes itself (lean kernel; on one device always, across devices once
@@ -836,11 +863,16 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2)); CK(cudaEventCreate(&e3));
     float t_th = 0, t_rhs = 0, t_h = 0;
     const int a = S->cur, b = (S->cur + 1) % S->nstate;
-    StageCoef c = {0.0, 0, 0, 0, 1};     // cN = 0: the state is copied through unchanged, so reps do not drift
+    // the most frequent stage shape of the solver's scheme, with coefficients that leave state and registers unchanged (reps do not
+    // drift): low-storage RK3 stages 2-3 (RA read, RW written); Kutta RK3 stage 2 (base != input, RA read, RW written); RK4
+    // stages 2-3 (base != input, RW accumulated)
+    const bool ls = S->P.lowStorage && !S->P.rk4;
+    StageCoef c = {0.0, 0, 0, 0, 1};
+    if (S->P.rk4) { c.wOld = 1.0; c.wNew = 0.0; }
     for (int r = 0; r < reps; r++) {
         CK(cudaEventRecord(e0, S->st));
-        StagePtrs p; p.qin = S->state[a]; p.qbase = S->state[a]; p.qout = S->state[b]; p.theta = S->theta;
-        p.RA = S->R1; p.RB = nullptr; p.RW = S->R1; p.rhs_out = nullptr;
+        StagePtrs p; p.qin = S->state[a]; p.qbase = ls ? S->state[a] : S->state[(a + 2) % 3]; p.qout = S->state[b]; p.theta = S->theta;
+        p.RA = S->P.rk4 ? nullptr : S->R1; p.RB = nullptr; p.RW = (ls || S->P.rk4) ? S->R1 : S->R2; p.rhs_out = nullptr;
         const bool fast = stage_is_fast(S, p, c);
         if (fast) {
             p.theta = S->state[a] + 7 * S->L.vol;
@@ -849,7 +881,7 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
         launch_theta(S->kc, S->state[a], const_cast<double *>(p.theta), S->st);
         CK(cudaEventRecord(e1, S->st));
         ghost_targets(S, b, p);
-        launch_stage_any(S, p, c, a, a);
+        launch_stage_any(S, p, c, a, ls ? a : (a + 2) % 3);
         S->aux_valid[b] = false;                          // a scratch copy of the state, never advanced from
         CK(cudaEventRecord(e2, S->st));
         if (inkernel_ghosts(S)) handshake(S);

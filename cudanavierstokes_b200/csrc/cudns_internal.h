@@ -106,6 +106,14 @@ struct FastMaps {
     CUtensorMap opa;                        // RA (unpadded register array, tile interior)
 };
 void launch_rhs_stage_fast(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, int ty, cudaStream_t st);
+// fifth-generation kernel (stage_duo.inc): tile 64 x 8, two x-adjacent points per thread; same 8-field state buffers; needs an even mx
+constexpr int DUO_TX = 64, DUO_TY = 8;
+struct DuoMaps {
+    CUtensorMap q4box, a3box;               // halo'd tile (72 x (8+2s)) of (rho,u,v,w) and of (H,T,theta)
+    CUtensorMap q4int, a3int;               // tile interior (64 x 8) of the same (plane S ahead, for the z ring)
+};
+void launch_rhs_stage_duo(const KConst &kc, const StagePtrs &p, const StageCoef &c, const DuoMaps &maps, cudaStream_t st);
+int duo_smem_bytes(int s);
 void launch_derive_aux(const KConst &kc, double *q8, cudaStream_t st);
 int fast_smem_bytes(int s, int ty);
 int lean_smem_wide_bytes(int s);

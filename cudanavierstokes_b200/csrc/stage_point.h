@@ -55,6 +55,30 @@ __device__ __forceinline__ void pair_step(const KConst &c, const int l, const do
         A.lapu[D] = fma(c.c1t[D][l], Pn[FD] - Mn[FD], A.lapu[D]);
     }
 }
+// one neighbour of direction D at offset +l (PLUS) or -l: the same sums, one side at a time (one more FP64 instruction per pair,
+// half the registers for neighbour values)
+template <int D, int V, bool PLUS>
+__device__ __forceinline__ void side_step(const KConst &c, const int l, const double (&C)[NF], const double (&Nq)[NF], Acc &A, double &aM) {
+    const double cC = c.cf[D][l][0];
+    const double cu = cC * C[FU + D];
+    const double Af = (C[FR] + Nq[FR]) * fma(cC, Nq[FU + D], cu);
+    const double pn = Nq[FR] * Nq[FT];
+    const double sA = PLUS ? Af : -Af;
+    aM += sA;
+    A.r[1] = fma(sA, Nq[FU], A.r[1]); A.r[2] = fma(sA, Nq[FV], A.r[2]); A.r[3] = fma(sA, Nq[FW], A.r[3]); A.r[4] = fma(sA, Nq[FH], A.r[4]);
+    A.r[1 + D] = fma(PLUS ? c.cfp[D][l] : -c.cfp[D][l], pn, A.r[1 + D]);
+    if (l <= V) {
+        const double k1 = PLUS ? c.cf[D][l][2] : -c.cf[D][l][2], k2 = c.cf[D][l][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            A.g[D][m] = fma(k1, Nq[FU + m], A.g[D][m]);
+            A.lapu[m] = fma(k2, Nq[FU + m], A.lapu[m]);
+        }
+        A.dT[D] = fma(k1, Nq[FT], A.dT[D]);
+        A.lapT = fma(k2, Nq[FT], A.lapT);
+        A.lapu[D] = fma(PLUS ? c.c1t[D][l] : -c.c1t[D][l], Nq[FD], A.lapu[D]);
+    }
+}
 // the direction is complete: central values times its mass-flux sum
 __device__ __forceinline__ void close_dir(const double (&C)[NF], Acc &A, const double aM) {
     A.r[0] = fma(2.0, aM, A.r[0]);

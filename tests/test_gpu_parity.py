@@ -119,6 +119,21 @@ def test_narrow_tile_variant_of_the_stage_kernel(sv, monkeypatch):
     assert max(errs) < TOL, errs
 
 
+@pytest.mark.parametrize("scheme", ["lowstorage", "kutta", "rk4"])
+@pytest.mark.parametrize("sv", [(1, 1), (2, 1), (3, 2), (4, 2), (4, 4)])
+def test_duo_kernel_all_schemes_and_stencils(sv, scheme, monkeypatch):
+    """every Runge-Kutta stage shape (base state != input state, second operand, accumulated register) on the fifth-generation
+    kernel, ragged 64 x 8 tiles (mx = 70: three active lanes in the second tile column) and two z chunks"""
+    monkeypatch.setenv("CUDNS_DUO", "1")            # (the default for Kutta RK3 / RK4; low-storage RK3 would take the fourth generation)
+    op = ob.params_tgv(24, sv[0], stencilVisc=sv[1], mx=70, my=12, mz=64, Lx=3.0, Ly=5.0, Lz=4.0,
+                       lowStorage=int(scheme == "lowstorage"), rk4=int(scheme == "rk4"))
+    o, s, grid = make_pair(op)
+    st = smooth_random_state(o); o.set_state(st); s.set_state(st)
+    o.run(6); s.advance(6)
+    errs = [relerr(a, b) for a, b in zip(conserved(s.get_state()), conserved(o.state()))]
+    assert max(errs) < TOL, errs
+
+
 @pytest.mark.parametrize("shape", [(40, 20, 24), (24, 36, 16), (70, 10, 12), (32, 8, 72)])
 def test_fast_kernel_ragged_tiles_and_z_chunks(shape):
     """linear viscosity + periodic box = the fourth-generation stage kernel (8-field state buffers, H and T written with the
@@ -134,7 +149,7 @@ def test_fast_kernel_ragged_tiles_and_z_chunks(shape):
 
 
 def _advance_with_env(monkeypatch, env, nsteps, sv=(4, 4)):
-    for k in ("CUDNS_WIDE", "CUDNS_FAST_TY"):
+    for k in ("CUDNS_WIDE", "CUDNS_FAST_TY", "CUDNS_DUO"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -146,12 +161,17 @@ def _advance_with_env(monkeypatch, env, nsteps, sv=(4, 4)):
 
 
 def test_stage_kernel_generations_agree(monkeypatch):
-    """the same 12 Taylor-Green steps through the fast kernel with its 8-warp and its 16-warp tile (identical arithmetic per
-    point: bit for bit), and through the lean wide / lean kernels (p staged instead of rebuilt from rho*T: round-off)"""
-    a8 = _advance_with_env(monkeypatch, {}, 12)
+    """the same 12 Taylor-Green steps through the fifth-generation kernel (two points per thread, the default), the fourth generation
+    with its 8-warp and its 16-warp tile (identical arithmetic per point: bit for bit), and through the lean wide / lean kernels
+    (p staged instead of rebuilt from rho*T: round-off)"""
+    a5 = _advance_with_env(monkeypatch, {"CUDNS_DUO": "1"}, 12)
+    a8 = _advance_with_env(monkeypatch, {"CUDNS_DUO": "0"}, 12)
     a16 = _advance_with_env(monkeypatch, {"CUDNS_FAST_TY": "16"}, 12)
     for x, y in zip(a8, a16):
         assert np.array_equal(x, y)
+    # the fifth generation sums the x and y neighbours one side at a time (half the registers in flight): round-off
+    errs = [relerr(x, y) for x, y in zip(a5, a8)]
+    assert max(errs) < TOL, errs
     for env in ({"CUDNS_WIDE": "1"}, {"CUDNS_WIDE": "0"}):
         b = _advance_with_env(monkeypatch, env, 12)
         errs = [relerr(x, y) for x, y in zip(a8, b)]
