@@ -15,7 +15,14 @@ scaling); the stage kernel stores its boundary planes straight into the neighbou
 (CUDA IPC handles swapped once through torch.distributed), scalar reductions go through NCCL on the solver's stream.
 
 --impl reference: the reference has no CPU implementation; the arm times the CPU oracle
-(oracle/, an OpenMP restatement of the reference's algorithm, kind "port") on this box's host cores.
+(oracle/, an OpenMP restatement of the reference's algorithm, kind "port") on this box's host cores, every host
+thread (OMP_NUM_THREADS is overridden: torch.distributed.run exports 1), on a bounded sample of the SAME workload:
+full 512 x 512 planes of the same grid spacing, stencil and scheme, a slab of --ref-planes planes instead of 512.
+
+The bench line also carries: `roofline` of the stage kernel (burst time of isolated launches AND the time of the same
+kernel inside the step loop, CUDA events around every stage), `schemes.rk4` = the same measurement for the classical
+RK4 step north_star names (200 algorithmic bytes per point-stage), `ref_gpu_baseline` = the reference's own GPU build
+(oracle/_ref/perf512_*) run in the same job, `cpu_baseline`, `e2e`, `clocks`.
 """
 import argparse
 import json
@@ -121,46 +128,91 @@ def tgv_slab(out, grid, p, k0, mzl):
         e[a:b] = press / (p.gam - 1.0) + 0.5 * r[a:b] * (u[a:b] * u[a:b] + v[a:b] * v[a:b])
 
 
-def cpu_oracle_rate(scheme, budget_s=12.0, n=128):
-    """time the CPU oracle (all host threads) on a bounded sample of the workload: same physics/stencil, n^3 grid"""
+def make_config(n, scheme, world):
+    """the `config` object of the bench line -- built by one function so that both arms print the same"""
+    npts = float(n) ** 3
+    return {"workload": "tgv%d_s4v4_fp64_%s" % (n, scheme), "grid": [n, n, n], "scheme": scheme, "stages_per_step": STAGES[scheme],
+            "stencilSize": 4, "stencilVisc": 4, "decomposition": "z-slabs x%d" % world,
+            "halo": ("peer-memory stores from the stage kernel over NVLink (CUDA IPC) + device-side epoch flags"
+                     if world > 1 else "periodic z wrap stored by the stage kernel"),
+            "cache": "inputs larger than L2 (each of the >=22 resident fields is %.2f GiB per GPU)" % (npts * 8 / world / 2 ** 30)}
+
+
+def oracle_slab(n, planes, scheme):
+    """the CPU oracle on a bounded sample of the n^3 workload: full n x n planes, same grid spacing / stencil / scheme, `planes`
+    planes in z (periodic).  Returns (oracle, points)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import math
     import oracle_binding as ob
-    op = ob.params_tgv(n, 4, lowStorage=int(scheme == "ls3"), rk4=int(scheme == "rk4"))
+    threads = ob.set_threads()                       # every core this process may run on, whatever OMP_NUM_THREADS says
+    op = ob.params_tgv(n, 4, mz=planes, Lz=2 * math.pi * planes / n, lowStorage=int(scheme == "ls3"), rk4=int(scheme == "rk4"))
     o = ob.Oracle(op); o.init_chit()
+    return o, n * n * planes, threads
+
+
+def cpu_oracle_rate(scheme, n, planes, budget_s=12.0):
+    """time the CPU oracle (all host threads) on the slab sample of the workload for about budget_s seconds"""
+    o, pts, threads = oracle_slab(n, planes, scheme)
     t0 = time.perf_counter(); o.run(1); t1 = time.perf_counter() - t0
     steps = max(1, min(40, int(budget_s / max(t1, 1e-3))))
     t0 = time.perf_counter(); o.run(steps); dt = time.perf_counter() - t0
     o.close()
-    rate = n ** 3 * STAGES[scheme] * steps / dt / 1e6
-    return rate, steps, dt, n
+    return pts * STAGES[scheme] * steps / dt / 1e6, steps, dt, threads
+
+
+def ref_gpu_baseline(n, scheme, root=ROOT):
+    """the reference's OWN GPU build (oracle/_ref/perf<n>_n<steps>, compiled from the unmodified sources by oracle/refbuild/, sm_100
+    recompile) run on this GPU: two run lengths, per-step time from the difference of the whole-run wall times it prints (set-up and
+    fields/ I/O cancel).  None when the binaries are not there or the scheme is not the reference's default."""
+    import glob, re, shutil, tempfile
+    if scheme != "ls3":
+        return {"unavailable": "the reference binaries are built for its default scheme (low-storage RK3)"}
+    bins = sorted(glob.glob(os.path.join(root, "oracle", "_ref", "perf%d_n*" % n)), key=lambda b: int(b.rsplit("_n", 1)[1]))
+    if len(bins) < 2:
+        return {"unavailable": "oracle/_ref/perf%d_n* not built (needs /root/reference at build time)" % n}
+    runs = []
+    for b in (bins[0], bins[-1]):
+        d = tempfile.mkdtemp(prefix="refperf.")
+        os.makedirs(os.path.join(d, "fields"))
+        try:
+            out = subprocess.run([b], cwd=d, capture_output=True, text=True, timeout=600).stdout
+        except Exception as e:       # noqa: BLE001
+            shutil.rmtree(d, ignore_errors=True)
+            return {"unavailable": "running %s failed: %s" % (os.path.basename(b), e)}
+        shutil.rmtree(d, ignore_errors=True)
+        m = re.search(r"The total time is\D*([0-9.eE+-]+)", out)
+        if not m:
+            return {"unavailable": "no wall time in the output of %s" % os.path.basename(b)}
+        runs.append((int(b.rsplit("_n", 1)[1]), float(m.group(1))))
+    (n0, t0), (n1, t1) = runs
+    ms = (t1 - t0) / (n1 - n0) * 1e3
+    return {"value": float(n) ** 3 * 3 / (ms * 1e-3) / 1e6, "unit": "Mpts*RK-stage/s", "ms_per_step": ms,
+            "how": "oracle/_ref/%s and %s (unmodified reference kernels, sm_100): (%.2f s - %.2f s) / (%d - %d steps)" %
+                   (os.path.basename(bins[-1]), os.path.basename(bins[0]), t1, t0, n1, n0)}
 
 
 def run_reference(args):
-    """--impl reference: the oracle port on the host cores; each "step" = a bounded sample (one time step of the n=128
-    sub-problem)."""
+    """--impl reference: the oracle port on the host cores; each "step" = one time step of the bounded sample (a slab of full
+    n x n planes of the same workload)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_binding as ob
-    n = args.ref_n
-    scheme = args.scheme
-    op = ob.params_tgv(n, 4, lowStorage=int(scheme == "ls3"), rk4=int(scheme == "rk4"))
-    o = ob.Oracle(op); o.init_chit()
+    n, scheme = args.n, args.scheme
+    o, pts, threads = oracle_slab(n, args.ref_planes, scheme)
     for _ in range(args.warmup):
         o.run(1)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         o.run(1)
     dt = time.perf_counter() - t0
-    cores = os.cpu_count()
-    val = n ** 3 * STAGES[scheme] * args.steps / dt / 1e6
-    sample = "TGV %d^3 (same physics, stencil and scheme as the %d^3 workload), 1 time step per bench step" % (n, args.n)
+    val = pts * STAGES[scheme] * args.steps / dt / 1e6
+    sample = ("CPU oracle (OpenMP restatement of the reference, %d host threads) on a %d x %d x %d slab of the %d^3 workload "
+              "(same grid spacing, stencil, scheme; periodic in z), 1 time step per bench step" % (threads, n, n, args.ref_planes, n))
     line = {"impl": "reference", "metric": "Mpts*RK-stage/s", "value": val, "unit": "Mpts*RK-stage/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "tgv%d_s4v4_fp64_%s" % (args.n, scheme), "scheme": scheme, "stencilSize": 4, "stencilVisc": 4},
-            "cpu_baseline": {"value": val, "unit": "Mpts*RK-stage/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(n, scheme, args.gpus), "sample_grid": [n, n, args.ref_planes],
+            "cpu_baseline": {"value": val, "unit": "Mpts*RK-stage/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mpts*RK-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -176,7 +228,9 @@ def main():
                     "treats a bare --n as an abbreviation of its own options)")
     ap.add_argument("--scheme", default="ls3", choices=sorted(STAGES))
     ap.add_argument("--impl", default="cudns", choices=["cudns", "reference"])
-    ap.add_argument("--ref-n", type=int, default=128)
+    ap.add_argument("--ref-planes", type=int, default=32, help="planes of the CPU sample slab (full n x n planes each)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the run of the reference's own GPU build (about 2 minutes)")
+    ap.add_argument("--no-schemes", action="store_true", help="skip the additional RK4 measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -202,23 +256,10 @@ def main():
     if world != args.gpus and rank == 0:
         print("warning: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
-    n, scheme = args.n, args.scheme
-    stages = STAGES[scheme]
-    p = scheme_params(cd, n, scheme)
-    p.nranks = world; p.rank = rank; p.device = local
-    grid = cd.init_grid(p)
-    sol = cd.Solver(p, grid)
-    if world > 1:
-        from cudanavierstokes_b200 import dist as cdist
-        cdist.attach(sol)
+    n = args.n
+    npts = float(n) ** 3
     mzl = n // world
-    # Taylor-Green initial condition of this rank's slab (the formulas of initCHIT, init.cpp:126-148, vectorised)
-    pin = torch.empty((5, mzl, n, n), dtype=torch.float64).pin_memory()
-    host = pin.numpy()
-    tgv_slab(host, grid, p, rank * mzl, mzl)
-    views = [host[f] for f in range(5)]
-    sol.set_state(views)
-    stream = torch.cuda.ExternalStream(sol.stream(), device=torch.device("cuda", local))
+    peak, peak_kind = measured_peak()
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,48 +267,85 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sol.advance(args.warmup, history=False)
-    c0 = sol.counters()
-    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    ev0.record(stream)
-    sol.advance(args.steps, history=False)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    c1 = sol.counters()
-    if dist is not None:                                           # max over ranks (also: every rank must derive the same `extra`)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    # nvidia-smi delivers a sample every ~100 ms: when the timed region was shorter than that (many GPUs, small K), the same
-    # workload keeps running untimed until the sampler has seen it for ~0.8 s, so the clocks line describes this load
-    extra = 0
-    if ms < 800.0:
-        extra = int((800.0 - ms) / max(ms / args.steps, 1e-3)) + 1
-        sol.advance(extra, history=False)
-        barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["covers"] = "timed region" if extra == 0 else "timed region + %d untimed steps of the same workload" % extra
-    npts = float(n) ** 3
-    value = npts * stages * args.steps / (ms * 1e-3) / 1e6          # Mpts*stage/s, whole job
-    launches = int(c1["kernel_launches"] - c0["kernel_launches"])
+        return float(t.item())
 
-    # ---- per-kernel device time of one stage (CUDA events on the solver's stream, inside the library)
-    prof = sol.profile_stage(5)
-    peak, peak_kind = measured_peak()
-    alg = ALG_BYTES[scheme] * npts / world                           # bytes per launch of the stage kernel on one rank
-    ach = alg / (prof["rhs_stage_ms"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fast::stage_kernel (fused RHS + RK stage update + H,T of the new state + halo stores)", "achieved": ach, "peak": peak, "peak_kind": peak_kind,
-                "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("rhs_stage_%d" % n),
-                "alg_bytes_per_launch": alg, "kernel_ms": prof["rhs_stage_ms"], "theta_ms": prof["theta_ms"],
-                "zghost_ms": prof["halo_ms"],
-                # whole step (dilatation pass, reductions, hand-shake included), per GPU against one GPU's peak
-                "whole_step_achieved": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world, "whole_step_frac": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world / peak}
+    # Taylor-Green initial condition of this rank's slab (the formulas of initCHIT, init.cpp:126-148, vectorised), pinned host memory
+    p0 = scheme_params(cd, n, args.scheme)
+    p0.nranks = world; p0.rank = rank; p0.device = local
+    grid = cd.init_grid(p0)
+    pin = torch.empty((5, mzl, n, n), dtype=torch.float64).pin_memory()
+    host = pin.numpy()
+    tgv_slab(host, grid, p0, rank * mzl, mzl)
+    views = [host[f] for f in range(5)]
+
+    def measure(scheme, steps, warmup, with_clocks):
+        """one solver of `scheme`: K timed steps between CUDA events on the solver's stream (max over ranks), then the same K steps
+        again with CUDA events around every stage (kernel times under the sustained load of the step loop), then isolated launches"""
+        stages = STAGES[scheme]
+        p = scheme_params(cd, n, scheme)
+        p.nranks = world; p.rank = rank; p.device = local
+        sol = cd.Solver(p, grid)
+        if world > 1:
+            from cudanavierstokes_b200 import dist as cdist
+            cdist.attach(sol)
+        sol.set_state(views)
+        stream = torch.cuda.ExternalStream(sol.stream(), device=torch.device("cuda", local))
+        sol.advance(warmup, history=False)
+        c0 = sol.counters()
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if with_clocks else None
+        barrier()
+        if sampler is not None and rank == 0:
+            sampler.start()
+        ev0.record(stream)
+        sol.advance(steps, history=False)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        c1 = sol.counters()
+        # the same steps once more, back to back, with events around the dilatation pass / stage kernel / hand-shake of every stage:
+        # the kernels' durations under the conditions of the timed region (clocks under the power cap); nvidia-smi also needs
+        # ~0.8 s of this load to deliver samples when the timed region was short (every rank derives the same count from `ms`)
+        extra = max(steps, int(800.0 / max(ms / steps, 1e-3)) + 1 if ms < 800.0 else steps)
+        sol.stage_timing(True)
+        done = 0
+        while done < extra:
+            m = min(extra - done, 1024 // stages)
+            sol.advance(m, history=False); done += m
+        sust = sol.stage_timing()
+        sol.stage_timing(False)
+        barrier()
+        clocks = sampler.stop() if (sampler is not None and rank == 0) else None
+        if clocks is not None:
+            clocks["covers"] = "timed region + %d steps of the same workload with per-stage events" % extra
+        prof = sol.profile_stage(5)
+        value = npts * stages * steps / (ms * 1e-3) / 1e6          # Mpts*stage/s, whole job
+        alg = ALG_BYTES[scheme] * npts / world                      # algorithmic bytes per launch of the stage kernel on one rank
+        k_sust = max_over_ranks(sust["rhs_stage_ms"]); k_burst = max_over_ranks(prof["rhs_stage_ms"])
+        kernel = ("duo::stage_kernel<4,4> (two points per thread)" if (scheme != "ls3" or os.environ.get("CUDNS_DUO") == "1")
+                  else "fast::stage_kernel<4,4,8>") + ": fused RHS + RK stage update + H,T of the new state + halo stores"
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": alg / (k_sust * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind,
+                    "unit": "GB/s", "frac": alg / (k_sust * 1e-3) / 1e9 / peak,
+                    "traffic": ncu_traffic("rhs_stage_%d_%s" % (n, scheme)) if world == 1 else None,
+                    "alg_bytes_per_launch": alg, "alg_bytes_per_point": ALG_BYTES[scheme],
+                    "kernel_ms": k_sust, "kernel_ms_how": "mean over %d launches inside the step loop (CUDA events around every stage, sustained clocks)" % sust["stages"],
+                    "kernel_ms_burst": k_burst, "frac_burst": alg / (k_burst * 1e-3) / 1e9 / peak,
+                    "kernel_ms_burst_how": "5 isolated launches of the scheme's most frequent stage shape (cudns_profile_stage)",
+                    "theta_ms": max_over_ranks(sust["theta_ms"]), "theta_ms_burst": prof["theta_ms"], "handshake_ms": max_over_ranks(sust["halo_ms"]),
+                    # whole step (dilatation pass, reductions, hand-shake included), per GPU against one GPU's peak
+                    "whole_step_achieved": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world,
+                    "whole_step_frac": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world / peak}
+        return sol, {"value": value, "ms_per_step": ms / steps, "launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+                     "roofline": roofline, "clocks": clocks}
+
+    scheme = args.scheme
+    stages = STAGES[scheme]
+    sol, main_res = measure(scheme, args.steps, args.warmup, True)
 
     # ---- end to end through the C ABI with host buffers: copyField(0) + one step + copyField(1) per step
     e2e = None
@@ -282,33 +360,41 @@ def main():
             sol.advance(1, history=False)
             sol.get_state_into(oviews)
         barrier()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         nbytes = 5 * 8 * int(npts)
         e2e = {"value": npts * stages * args.e2e_steps / dt / 1e6, "unit": "Mpts*RK-stage/s", "steps": args.e2e_steps,
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "what": "cudns_set_state(pinned host) + cudns_advance(1) + cudns_get_state(pinned host) per step"}
+        del out, oviews
+    sol.close()
+
+    # ---- the classical RK4 step north_star names (an extension: the reference has Wray and Kutta RK3 only), same grid and stencil
+    schemes = None
+    if not args.no_schemes and scheme != "rk4":
+        s4, r4 = measure("rk4", args.steps, args.warmup, False)
+        s4.close()
+        schemes = {"rk4": {"config": make_config(n, "rk4", world), "value": r4["value"], "unit": "Mpts*RK-stage/s", "ms_per_step": r4["ms_per_step"],
+                           "stages_per_step": 4, "roofline": r4["roofline"], "gpu_launches": r4["launches"]}}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        rate, steps, dt, nn = cpu_oracle_rate(scheme)
-        cpu = {"value": rate, "unit": "Mpts*RK-stage/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "CPU oracle (OpenMP, all host threads), TGV %d^3 same stencil/scheme, %d steps in %.1f s" % (nn, steps, dt)}
+    refgpu = None
+    if rank == 0 and world == 1:
+        if not args.no_cpu:
+            rate, steps, dt, threads = cpu_oracle_rate(scheme, n, args.ref_planes)
+            cpu = {"value": rate, "unit": "Mpts*RK-stage/s", "cores": threads, "kind": "port",
+                   "sample": "CPU oracle (OpenMP, %d host threads) on a %d x %d x %d slab of the workload, same stencil/scheme, %d steps in %.1f s" %
+                             (threads, n, n, args.ref_planes, steps, dt)}
+        if not args.no_ref_gpu:
+            torch.cuda.empty_cache()
+            refgpu = ref_gpu_baseline(n, scheme)
     if rank == 0:
-        line = {"metric": "Mpts*RK-stage/s", "value": value, "unit": "Mpts*RK-stage/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "tgv%d_s4v4_fp64_%s" % (n, scheme), "grid": [n, n, n], "scheme": scheme,
-                           "stages_per_step": stages, "stencilSize": 4, "stencilVisc": 4, "decomposition": "z-slabs x%d" % world,
-                           "halo": ("peer-memory stores from the stage kernel over NVLink (CUDA IPC) + device-side epoch flags"
-                                    if world > 1 else "periodic z wrap stored by the stage kernel"),
-                           "cache": "inputs larger than L2 (each of the >=22 resident fields is %.2f GiB per GPU)" % (npts * 8 / world / 2 ** 30)},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-                "hbm_gbs_whole_step": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world}
+        line = {"metric": "Mpts*RK-stage/s", "value": main_res["value"], "unit": "Mpts*RK-stage/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": make_config(n, scheme, world),
+                "roofline": main_res["roofline"], "cpu_baseline": cpu, "ref_gpu_baseline": refgpu, "e2e": e2e,
+                "gpu_launches": main_res["launches"], "clocks": main_res["clocks"], "schemes": schemes,
+                "hbm_gbs_whole_step": ALG_BYTES[scheme] * main_res["value"] * 1e6 / 1e9 / world}
         print(json.dumps(line), flush=True)
-    sol.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

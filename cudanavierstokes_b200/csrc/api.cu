@@ -112,6 +112,8 @@ struct cudns_solver {
     bool aux_valid[3];           // H, T of state[b] (ghosts included) match its (rho,u,v,w,rho*E)
     bool duo;                    // the fifth-generation kernel (stage_duo.inc) serves EVERY stage of this configuration (CUDNS_DUO=0: off)
     DuoMaps dmaps[3];            // its TMA descriptors per state buffer
+    bool theta_tma;              // the dilatation pass runs its TMA variant (periodic / uniform set-ups, even mx; CUDNS_THETA_TMA=0: off)
+    ThetaMaps tmaps[3];          // u, v, w boxes of every state buffer
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libcudns does not link libcuda)
@@ -318,6 +320,19 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
                 }
             }
             if ((rc = make_rmap(&S->frmap[0], L, S->R1, fty)) || (S->R2 && (rc = make_rmap(&S->frmap[1], L, S->R2, fty)))) { cudns_destroy(S); return rc; }
+        }
+        {
+            const char *te = getenv("CUDNS_THETA_TMA");
+            S->theta_tma = p->periodicX && !p->nonUniformX && !p->boundaryLayer && mx % 2 == 0 && !(te && std::string(te) == "0") &&
+                           (size_t)theta_tma_smem_bytes(v) <= prop.sharedMemPerBlockOptin;
+            for (int b = 0; S->theta_tma && b < S->nstate; b++) {
+                double *q = S->state[b];
+                if ((rc = make_map(&S->tmaps[b].u, L, q + L.vol, 1, THETA_TX + 2 * GX, THETA_TY)) ||
+                    (rc = make_map(&S->tmaps[b].v, L, q + 2 * L.vol, 1, THETA_TX, THETA_TY + 2 * v)) ||
+                    (rc = make_map(&S->tmaps[b].w, L, q + 3 * L.vol, 1, THETA_TX, THETA_TY))) {
+                    cudns_destroy(S); return rc;
+                }
+            }
         }
         if (S->duo) {
             const int DXb = DUO_TX + 2 * GX, DYb = DUO_TY + 2 * s;
@@ -643,7 +658,8 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     StageTimer *tm = (S->tm && S->tm->on && !rhs_out && S->tm->used + 4 <= S->tm->ev.size()) ? S->tm : nullptr;
     cudaEvent_t *tev = tm ? &tm->ev[tm->used] : nullptr;
     if (tm) { tm->used += 4; cudaEventRecord(tev[0], S->st); }
-    launch_theta(S->kc, S->state[in], const_cast<double *>(p.theta), S->st);
+    if (S->theta_tma) launch_theta_tma(S->kc, S->state[in], const_cast<double *>(p.theta), S->tmaps[in], S->st);
+    else launch_theta(S->kc, S->state[in], const_cast<double *>(p.theta), S->st);
     if (tm) cudaEventRecord(tev[1], S->st);
     ghost_targets(S, out, p);
     if (rhs_out) { p.qout_lo = nullptr; p.qout_hi = nullptr; }
@@ -878,7 +894,8 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
             p.theta = S->state[a] + 7 * S->L.vol;
             if (!S->aux_valid[a]) { launch_derive_aux(S->kc, S->state[a], S->st); S->aux_valid[a] = true; }
         }
-        launch_theta(S->kc, S->state[a], const_cast<double *>(p.theta), S->st);
+        if (S->theta_tma) launch_theta_tma(S->kc, S->state[a], const_cast<double *>(p.theta), S->tmaps[a], S->st);
+        else launch_theta(S->kc, S->state[a], const_cast<double *>(p.theta), S->st);
         CK(cudaEventRecord(e1, S->st));
         ghost_targets(S, b, p);
         launch_stage_any(S, p, c, a, ls ? a : (a + 2) % 3);

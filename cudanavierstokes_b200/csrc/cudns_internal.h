@@ -121,6 +121,12 @@ int lean_smem_wide_bytes(int s);
 int lean_smem_bytes(int s, bool linear_visc);
 
 void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st);
+// TMA variant of the dilatation pass (theta.cu) for the periodic / uniform set-ups with an even mx: boxes of u (72 x 16, x halos),
+// v (64 x (16 + 2v), y halos) and w (64 x 16) of one padded state buffer
+constexpr int THETA_TX = 64, THETA_TY = 16;
+struct ThetaMaps { CUtensorMap u, v, w; };
+void launch_theta_tma(const KConst &kc, const double *q, double *theta, const ThetaMaps &maps, cudaStream_t st);
+int theta_tma_smem_bytes(int v);
 void launch_fill_xy(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_zwrap(const KConst &kc, double *q5, int nfields, cudaStream_t st);
 void launch_pack_z(const KConst &kc, const double *q5, double *send_lo, double *send_hi, cudaStream_t st);
