@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("CUDNS_LIB", os.path.join(_HERE, "libcudns.so"))   # o
 CSRC = os.path.join(_HERE, "csrc")
 
 __all__ = ["Params", "PeerInfo", "Solver", "CudnsError", "lib", "build", "params_tgv", "params_channel", "params_blayer",
-           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "write_xdmf", "blasius_profiles", "EXPORTS"]
+           "init_grid", "init_chit", "init_channel", "build_sponge", "write_field", "read_field", "write_xdmf", "blasius_profiles", "stats_write", "EXPORTS"]
 
 # every symbol include/cudns.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -32,7 +32,9 @@ EXPORTS = [
     "cudns_set_exchange", "cudns_get_stream", "cudns_get_counters", "cudns_profile_stage",
     "cudns_set_stage_timing", "cudns_get_stage_timing",
     "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
-    "cudns_calc_profiles", "cudns_calc_retau", "cudns_blasius_profiles",
+    "cudns_calc_profiles", "cudns_calc_retau", "cudns_blasius_profiles", "cudns_calc_enstrophy",
+    "cudns_stats_begin", "cudns_stats_add_mean", "cudns_stats_finish_mean", "cudns_stats_add_fluc", "cudns_stats_get",
+    "cudns_stats_write", "cudns_postprocess",
 ]
 
 
@@ -59,7 +61,7 @@ class Params(C.Structure):
         ("amp1", C.c_double), ("amp2", C.c_double), ("omega1", C.c_double), ("omega2", C.c_double),
         ("quirk_q1", C.c_int), ("rk4", C.c_int),
         ("nranks", C.c_int), ("rank", C.c_int), ("device", C.c_int),
-        ("reserved", C.c_int * 5),
+        ("par2_enstrophy", C.c_int), ("reserved", C.c_int * 4),
     ]
 
 
@@ -140,6 +142,13 @@ def lib():
     L.cudns_calc_profiles.argtypes = [H, dp]
     L.cudns_blasius_profiles.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, dp, dp, dp, dp, dp]
     L.cudns_calc_retau.argtypes = [H, dp]
+    L.cudns_calc_enstrophy.argtypes = [H, dp]
+    L.cudns_stats_begin.argtypes = [H, C.c_int]
+    for name in ("cudns_stats_add_mean", "cudns_stats_finish_mean", "cudns_stats_add_fluc"):
+        getattr(L, name).argtypes = [H]
+    L.cudns_stats_get.argtypes = [H, dp, dp, dp, dp, dp]
+    L.cudns_stats_write.argtypes = [C.c_char_p, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double]
+    L.cudns_postprocess.argtypes = [H, C.c_char_p, C.c_int, C.c_int, dp, C.c_char_p]
     L.cudns_io_wait.argtypes = [H, C.POINTER(C.c_uint64)]
     L.cudns_read_fields.argtypes = [H, C.c_char_p, C.c_int]
     L.cudns_write_xdmf.argtypes = [C.c_char_p, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_char_p]
@@ -228,6 +237,12 @@ def blasius_profiles(gam=1.4, Ma=0.35, Pr=0.75, n=1000):
     out = [np.zeros(n) for _ in range(5)]
     _check(lib().cudns_blasius_profiles(gam, Ma, Pr, n, *[_dp(a) for a in out]))
     return out
+
+
+def stats_write(outdir, x, mean, fluc, bulk, retau, utau):
+    """mean.txt, fluc.txt, bulk.txt in the format of the reference's post-processing tool (Variables::printFile, post.cpp:61-86)"""
+    a = [np.ascontiguousarray(q, dtype=np.float64) for q in (x, mean, fluc, bulk)]
+    _check(lib().cudns_stats_write(str(outdir).encode(), a[0].size, *[_dp(q) for q in a], float(retau), float(utau)))
 
 
 def write_xdmf(path, x, y, z, timesteps, dt, names="ruvwe", single_precision=False):
@@ -352,6 +367,29 @@ class Solver:
         v = C.c_double(0.0)
         _check(self.L.cudns_calc_retau(self.h, C.byref(v)))
         return v.value
+
+    def enstrophy(self):
+        """mean square vorticity <w.w> of a periodic box (the dissipation measure of a Taylor-Green run; extension)"""
+        v = C.c_double(0.0)
+        _check(self.L.cudns_calc_enstrophy(self.h, C.byref(v)))
+        return v.value
+
+    def post_stats(self, snapshots):
+        """postproc/post.cpp over a list of (local-slab) states, reduced on the device: dict(mean[13][mx], fluc[13][mx], bulk[13], Ret, ut)"""
+        _check(self.L.cudns_stats_begin(self.h, len(snapshots)))
+        for st in snapshots:
+            self.set_state(st); _check(self.L.cudns_stats_add_mean(self.h))
+        _check(self.L.cudns_stats_finish_mean(self.h))
+        for st in snapshots:
+            self.set_state(st); _check(self.L.cudns_stats_add_fluc(self.h))
+        mean = np.zeros((13, self.p.mx)); fluc = np.zeros((13, self.p.mx)); bulk = np.zeros(13)
+        a = C.c_double(0.0); b = C.c_double(0.0)
+        _check(self.L.cudns_stats_get(self.h, _dp(mean), _dp(fluc), _dp(bulk), C.byref(a), C.byref(b)))
+        return dict(mean=mean, fluc=fluc, bulk=bulk, Ret=a.value, ut=b.value)
+
+    def postprocess(self, directory, first, last, outdir):
+        """post.cpp's main(): statistics over fields/<c>.<first..last>.bin -> mean.txt, fluc.txt, bulk.txt in outdir"""
+        _check(self.L.cudns_postprocess(self.h, str(directory).encode(), int(first), int(last), _dp(self.grid["x"]), str(outdir).encode()))
 
     def write_fields_async(self, directory, timestep):
         """snapshot the current state into fields/{r,u,v,w,e}.<timestep>.bin without stalling the step loop"""

@@ -41,7 +41,7 @@ using namespace cudns;
 
 // device scalar slots
 enum { SC_DT = 0, SC_DPDZ, SC_TGPU, SC_TIME, SC_RED0, SC_RED1, SC_STALE0, SC_STALE1, SC_BULK0, SC_BULK1, SC_BULK2, SC_BULK3,
-       SC_HALOERR /* u64: stage number of a hand-shake that timed out, 0 = none */, SC_N = 16 };
+       SC_HALOERR /* u64: stage number of a hand-shake that timed out, 0 = none */, SC_ENS /* mean square vorticity */, SC_N = 16 };
 
 // asynchronous fields/ writer: one snapshot in flight
 struct IoState {
@@ -93,6 +93,8 @@ struct cudns_solver {
     double *d_bulk;              // bulk_reduce_kernel scratch (block partials + completion counter), this solver's own
     unsigned long long halo_timeout_ns;
     double *d_prof;              // profile diagnostics scratch: partial[64][5][mx], mean[5][mx], var[5][mx], 1 scalar (lazy)
+    double *d_post;              // post-processing statistics: partial[64][13][mx], mean[13][mx], fluc[13][mx], bulk[13], Re_tau, u_tau (lazy)
+    int post_phase, post_files, post_added;   // 0 idle, 1 collecting means, 2 means final / collecting fluctuations, 3 fluctuations final
     double *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
     bool have_state, fixed_dt, have_sponge;
     cudns_allreduce_fn allreduce; void *allreduce_user;
@@ -372,7 +374,7 @@ int cudns_destroy(cudns_handle S) {
     cudaFree(S->block);
     cudaFree(S->theta); cudaFree(S->R1); cudaFree(S->R2);
     cudaFree(S->d_xp); cudaFree(S->d_cVSx); cudaFree(S->d_dxv); cudaFree(S->d_spx); cudaFree(S->d_spz); cudaFree(S->d_sref);
-    cudaFree(S->d_scal); cudaFree(S->d_hist); cudaFree(S->d_prof); cudaFree(S->d_bulk);
+    cudaFree(S->d_scal); cudaFree(S->d_hist); cudaFree(S->d_prof); cudaFree(S->d_post); cudaFree(S->d_bulk);
     cudaFree(S->send_lo); cudaFree(S->send_hi); cudaFree(S->recv_lo); cudaFree(S->recv_hi);
     if (S->tm) { for (auto &e : S->tm->ev) cudaEventDestroy(e); delete S->tm; }
     if (S->st) cudaStreamDestroy(S->st);
@@ -749,6 +751,24 @@ int cudns_calc_bulk(cudns_handle S, double *par1, double *par2) {
     return CUDNS_OK;
 }
 
+// mean square vorticity of a periodic box (see enstrophy_reduce_kernel): the dissipation history of the unforced runs
+static int enstrophy_supported(cudns_solver *S) {
+    if (!S->P.periodicX || S->P.boundaryLayer) { set_error("enstrophy: periodic boxes only (periodicX = 1, boundaryLayer = 0)"); return CUDNS_EUNSUPPORTED; }
+    return CUDNS_OK;
+}
+int cudns_calc_enstrophy(cudns_handle S, double *ens) {
+    if (!S || !ens) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
+    { int rc0 = enstrophy_supported(S); if (rc0) return rc0; }
+    CK(cudaSetDevice(S->P.device));
+    launch_enstrophy_reduce(S->kc, S->state[S->cur], S->d_scal + SC_ENS, S->d_bulk, S->st); S->launches++;
+    reduce_across(S, S->d_scal + SC_ENS, 1, 1);
+    CK(cudaStreamSynchronize(S->st));
+    CK(cudaMemcpy(ens, S->d_scal + SC_ENS, sizeof(double), cudaMemcpyDeviceToHost));
+    return CUDNS_OK;
+}
+
 // runSimulationLowStorage / runSimulation, cuda_main.cu:44-186
 int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double *par2) {
     if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
@@ -769,6 +789,8 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
     double *sc = S->d_scal;
     const cudns_params &P = S->P;
     const bool ls = P.lowStorage && !P.rk4;
+    const bool ens_hist = P.par2_enstrophy && !P.forcing;
+    if (ens_hist) { int rc0 = enstrophy_supported(S); if (rc0) return rc0; }
     for (int istep = 0; istep < nsteps; istep++) {
         // ---- calcTimeStepPressGrad, cuda_main.cu:249-265
         if (istep % P.checkCFLcondition == 0) {
@@ -796,6 +818,11 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
                 CK(cudaMemcpyAsync(h_p2 + istep, sc + SC_BULK3, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
             } else {
                 CK(cudaMemcpyAsync(h_p1 + istep, sc + SC_BULK0, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+                if (ens_hist) {                                                 // extension: par2 = <w.w> of the unforced periodic box
+                    launch_enstrophy_reduce(S->kc, S->state[S->cur], sc + SC_ENS, S->d_bulk, S->st); S->launches++;
+                    reduce_across(S, sc + SC_ENS, 1, 1);
+                    CK(cudaMemcpyAsync(h_p2 + istep, sc + SC_ENS, sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+                }
             }
         }
         const bool need_stale = !S->fixed_dt && (((istep + 1) % P.checkCFLcondition == 0) || istep == nsteps - 1);
@@ -842,7 +869,7 @@ int cudns_advance(cudns_handle S, int nsteps, double *time, double *par1, double
         CK(cudaMemcpy(b2.data(), h_p2, nsteps * sizeof(double), cudaMemcpyDeviceToHost));
         for (int i = 0; i < nsteps; i++) {
             if (par1 && i % P.checkBulk == 0) par1[i] = b1[i];
-            if (par2 && i % P.checkBulk == 0 && P.forcing) par2[i] = b2[i];
+            if (par2 && i % P.checkBulk == 0 && (P.forcing || ens_hist)) par2[i] = b2[i];
         }
     }
     return CUDNS_OK;
@@ -1105,6 +1132,111 @@ int cudns_calc_retau(cudns_handle S, double *retau) {
     CK(cudaMemcpyAsync(retau, out, sizeof(double), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
     return CUDNS_OK;
+}
+
+}  // extern "C"
+
+
+// ---- post-processing statistics: postproc/post.cpp as device reductions -----------------------------
+namespace {
+struct PostPtrs { double *partial, *mean, *fluc, *bulk, *ret; };
+PostPtrs post_ptrs(cudns_solver *S) {
+    PostPtrs p;
+    p.partial = S->d_post; p.mean = p.partial + post_partial_doubles(S->kc); p.fluc = p.mean + 13 * (size_t)S->L.mx;
+    p.bulk = p.fluc + 13 * (size_t)S->L.mx; p.ret = p.bulk + 13;
+    return p;
+}
+size_t post_doubles(cudns_solver *S) { return (size_t)post_partial_doubles(S->kc) + 26 * (size_t)S->L.mx + 16; }
+}  // namespace
+
+extern "C" {
+
+// main() of post.cpp up to the first loop (post.cpp:155-171): zero the accumulators; nsnapshots = endfile - initfile + 1
+int cudns_stats_begin(cudns_handle S, int nsnapshots) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (nsnapshots < 1) { set_error("nsnapshots < 1"); return CUDNS_EINVAL; }
+    CK(cudaSetDevice(S->P.device));
+    { int rc0 = need_allreduce(S); if (rc0) return rc0; }
+    if (!S->d_post) { int rc = dmalloc(S, &S->d_post, post_doubles(S)); if (rc) return rc; }
+    CK(cudaMemsetAsync(S->d_post, 0, post_doubles(S) * sizeof(double), S->st));
+    S->post_phase = 1; S->post_files = nsnapshots; S->post_added = 0;
+    return CUDNS_OK;
+}
+
+// calcState + addMean(mean) + addMean(bulk) + calcRet of the current state (post.cpp:173-179)
+int cudns_stats_add_mean(cudns_handle S) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (S->post_phase != 1) { set_error("cudns_stats_add_mean: call cudns_stats_begin first"); return CUDNS_ESTATE; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    if (S->post_added >= S->post_files) { set_error("cudns_stats_add_mean: more snapshots than cudns_stats_begin announced"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    const PostPtrs p = post_ptrs(S);
+    const double rows = (double)S->P.my * (double)S->P.mz;
+    launch_post_accumulate(S->kc, S->state[S->cur], nullptr, p.partial, p.mean, 1.0 / (rows * S->post_files), 0, S->st);
+    if (!S->P.periodicX && S->P.stencilSize <= 3)        // walls on both sides; the reference's index arithmetic leaves its array for s = 4
+        launch_post_ret(S->kc, S->state[S->cur], 1.0 / S->kc.d1[0], p.partial, p.ret, 1.0 / rows, S->st);
+    S->launches += 4; S->post_added++;
+    return CUDNS_OK;
+}
+
+// after the last snapshot: sums over the slabs, file averages, Favre division (post.cpp:180-187)
+int cudns_stats_finish_mean(cudns_handle S) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (S->post_phase != 1 || S->post_added != S->post_files) { set_error("cudns_stats_finish_mean: not every announced snapshot has been added"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    const PostPtrs p = post_ptrs(S);
+    reduce_across(S, p.mean, 13 * S->L.mx, 1);
+    reduce_across(S, p.ret, 2, 1);
+    launch_post_finish_mean(S->kc, p.mean, p.bulk, p.ret, 1.0 / S->post_files, S->st); S->launches++;
+    S->post_phase = 2; S->post_added = 0;
+    return CUDNS_OK;
+}
+
+// calcState + addFluc of the current state (post.cpp:188-192)
+int cudns_stats_add_fluc(cudns_handle S) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (S->post_phase != 2) { set_error("cudns_stats_add_fluc: call cudns_stats_finish_mean first"); return CUDNS_ESTATE; }
+    if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
+    if (S->post_added >= S->post_files) { set_error("cudns_stats_add_fluc: more snapshots than cudns_stats_begin announced"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    const PostPtrs p = post_ptrs(S);
+    launch_post_accumulate(S->kc, S->state[S->cur], p.mean, p.partial, p.fluc, 1.0 / ((double)S->P.my * (double)S->P.mz * S->post_files), 1, S->st);
+    S->launches += 2; S->post_added++;
+    return CUDNS_OK;
+}
+
+int cudns_stats_get(cudns_handle S, double *mean, double *fluc, double *bulk, double *retau, double *utau) {
+    if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
+    if (S->post_phase < 2) { set_error("cudns_stats_get: the means are not final (cudns_stats_finish_mean)"); return CUDNS_ESTATE; }
+    CK(cudaSetDevice(S->P.device));
+    const PostPtrs p = post_ptrs(S);
+    if (S->post_phase == 2 && S->post_added == S->post_files) { reduce_across(S, p.fluc, 13 * S->L.mx, 1); S->post_phase = 3; }
+    if (fluc && S->post_phase != 3) { set_error("cudns_stats_get: fluctuations requested before every snapshot went through cudns_stats_add_fluc"); return CUDNS_ESTATE; }
+    const size_t nb = 13 * (size_t)S->L.mx * sizeof(double);
+    if (mean) CK(cudaMemcpyAsync(mean, p.mean, nb, cudaMemcpyDeviceToHost, S->st));
+    if (fluc) CK(cudaMemcpyAsync(fluc, p.fluc, nb, cudaMemcpyDeviceToHost, S->st));
+    if (bulk) CK(cudaMemcpyAsync(bulk, p.bulk, 13 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    double r2[2] = {0, 0};
+    CK(cudaMemcpyAsync(r2, p.ret, 2 * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    if (retau) *retau = r2[0]; if (utau) *utau = r2[1];
+    return CUDNS_OK;
+}
+
+// the whole of post.cpp's main(): two passes over fields/<c>.<first..last>.bin of `dir`, then mean.txt, fluc.txt, bulk.txt into outdir
+int cudns_postprocess(cudns_handle S, const char *dir, int first, int last, const double *x, const char *outdir) {
+    if (!S || !x) { set_error("NULL argument"); return CUDNS_EINVAL; }
+    if (last < first) { set_error("cudns_postprocess: last < first"); return CUDNS_EINVAL; }
+    int rc = cudns_stats_begin(S, last - first + 1); if (rc) return rc;
+    for (int f = first; f <= last; f++) { rc = cudns_read_fields(S, dir, f); if (rc) return rc; rc = cudns_stats_add_mean(S); if (rc) return rc; }
+    rc = cudns_stats_finish_mean(S); if (rc) return rc;
+    for (int f = first; f <= last; f++) { rc = cudns_read_fields(S, dir, f); if (rc) return rc; rc = cudns_stats_add_fluc(S); if (rc) return rc; }
+    const int mx = S->L.mx;
+    std::vector<double> mean(13 * (size_t)mx), fluc(13 * (size_t)mx), bulk(13);
+    double ret = 0, ut = 0;
+    rc = cudns_stats_get(S, mean.data(), fluc.data(), bulk.data(), &ret, &ut); if (rc) return rc;
+    if (S->P.rank != 0) return CUDNS_OK;
+    return cudns_stats_write(outdir, mx, x, mean.data(), fluc.data(), bulk.data(), ret, ut);
 }
 
 }  // extern "C"

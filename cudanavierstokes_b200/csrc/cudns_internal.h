@@ -138,6 +138,8 @@ void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStrea
 // scratch: bulk_scratch_doubles() doubles owned by the calling solver (block partials, then the completion counter; zeroed once)
 void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, double *scratch, cudaStream_t st);
 int bulk_scratch_doubles();
+// mean square vorticity of a periodic box (same scratch)
+void launch_enstrophy_reduce(const KConst &kc, const double *q, double *out, double *scratch, cudaStream_t st);
 void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
 // wall-normal profiles / friction Reynolds number (calcAvgChan, printRes): see kernels.cu
 void launch_profile_partial(const KConst &kc, const double *q, const double *mean, double *partial, int pass, cudaStream_t st);
@@ -145,6 +147,11 @@ void launch_profile_combine(const KConst &kc, const double *partial, double *out
 void launch_profile_favre(const KConst &kc, double *mean, cudaStream_t st);
 int profile_partial_doubles(const KConst &kc);
 void launch_retau(const KConst &kc, const double *q, double *partial, double *out, double scale, cudaStream_t st);
+// post-processing statistics (postproc/post.cpp): see kernels.cu.  acc[13][mx] += scale * (sums | squared deviations from mean)
+int post_partial_doubles(const KConst &kc);
+void launch_post_accumulate(const KConst &kc, const double *q, const double *mean, double *partial, double *acc, double scale, int pass, cudaStream_t st);
+void launch_post_ret(const KConst &kc, const double *q, double host_dx, double *partial, double *ret2, double scale, cudaStream_t st);
+void launch_post_finish_mean(const KConst &kc, double *mean, double *bulk, double *ret2, double inv_files, cudaStream_t st);
 // cross-GPU stage hand-shake over peer memory: store `epoch` into the two neighbours' mailbox slots / spin until both own slots reach it
 void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st);
 // the wait gives up after timeout_ns (device global timer) and stores `epoch` into *err_word (0 = never timed out): a neighbour that

@@ -6,7 +6,9 @@
 //
 // keys: case=tgv|channel|blayer (presets of python-utils/CompNavierStokes.py, globals/channel.h, src/globals.h), every field of
 // cudns_params by name (mx, stencilSize, Re, ...), nsteps, nfiles, restartFile (-1: fresh start), outdir (default "."),
-// blasius=internal|<dir with {x,r,u,w,e}Prof.bin>, async_io=0|1, xdmf=0|1.
+// blasius=internal|<dir with {x,r,u,w,e}Prof.bin>, async_io=0|1, xdmf=0|1, par2_enstrophy=0|1 (Taylor-Green dissipation history in the
+// par2 column), post=<first>:<last> (no time stepping: the reference's post-processing tool postproc/post.cpp over the saved
+// fields/<c>.<first..last>.bin of outdir -> mean.txt, fluc.txt, bulk.txt there).
 // Outputs, in outdir, with the reference's names and formats: Grid.txt, fields/{x,y,z}.bin, fields/{r,u,v,w,e}.<%07d>.bin,
 // solution.txt, prof.txt (+ fields.xmf).  --dry-run stops before the GPU is touched (grid, initial condition, file 0).
 #include <cudns.h>
@@ -32,7 +34,7 @@ const Field kFields[] = {
     F_I(boundaryLayer), F_I(perturbed), F_I(forcing), F_I(periodicX), F_I(nonUniformX), F_I(checkCFLcondition), F_I(checkBulk),
     F_D(Re), F_D(Pr), F_D(Ma), F_D(viscexp), F_D(gam), F_D(stretch), F_D(TwallTop), F_D(TwallBot),
     F_D(spTopStr), F_D(spTopLen), F_D(spTopExp), F_D(spInlStr), F_D(spInlLen), F_D(spInlExp), F_D(spOutStr), F_D(spOutLen), F_D(spOutExp),
-    F_I(kC), F_I(LP), F_D(amp1), F_D(amp2), F_D(omega1), F_D(omega2), F_I(quirk_q1), F_I(rk4), F_I(device)};
+    F_I(kC), F_I(LP), F_D(amp1), F_D(amp2), F_D(omega1), F_D(omega2), F_I(quirk_q1), F_I(rk4), F_I(device), F_I(par2_enstrophy)};
 
 void die(const std::string &msg) { std::fprintf(stderr, "cudns_run: %s\n", msg.c_str()); std::exit(1); }
 #define CK(call) do { if ((call) != CUDNS_OK) die(std::string(#call) + ": " + cudns_last_error()); } while (0)
@@ -91,6 +93,7 @@ int main(int argc, char **argv) {
     const int restartFile = std::atoi(take("restartFile", "-1").c_str());
     const std::string outdir = take("outdir", "."), blasius = take("blasius", "internal");
     const bool async_io = std::atoi(take("async_io", "1").c_str()) != 0, xdmf = std::atoi(take("xdmf", "1").c_str()) != 0;
+    const std::string post = take("post", "");
     if (nsteps < 2 || nfiles < 1) die("nsteps must be >= 2 and nfiles >= 1");
 
     cudns_params P;
@@ -166,6 +169,15 @@ int main(int argc, char **argv) {
     // ---- setDevice + setGPUParameters + initSolver + copyField(0) (main.cpp:62-66)
     cudns_handle H;
     CK(cudns_create(&P, x.data(), xp.data(), xpp.data(), &H));
+    if (!post.empty()) {               // postproc/post.cpp:126-199 instead of the time loop
+        int first = 0, last = 0;
+        if (std::sscanf(post.c_str(), "%d:%d", &first, &last) != 2) die("post=<first>:<last> expected");
+        std::printf("Fields to postprocess :  %d -> %d\n", first, last);
+        CK(cudns_postprocess(H, outdir.c_str(), first, last, x.data(), outdir.c_str()));
+        CK(cudns_destroy(H));
+        std::printf("cudns_run: wrote mean.txt, fluc.txt, bulk.txt\n");
+        return 0;
+    }
     if (P.boundaryLayer) CK(cudns_set_sponge(H, sigx.data(), sigz.data(), ref5.data()));
     if (fresh) CK(cudns_set_state(H, r.data(), u.data(), v.data(), w.data(), e.data()));
     else CK(cudns_read_fields(H, outdir.c_str(), restartFile));

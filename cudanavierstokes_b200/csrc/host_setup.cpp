@@ -386,4 +386,31 @@ int cudns_write_xdmf(const char *path, int single_precision, const double *x, in
     return CUDNS_OK;
 }
 
+// Variables::printFile (post.cpp:61-86) for mean.txt, fluc.txt and bulk.txt: header with the friction Reynolds number and velocity,
+// the legend (the reference's own numbering, "13)" twice), then one %le row per wall-normal index: x and the 13 quantities
+static int write_stats_file(const std::string &path, int n, const double *x, const double *q, int stride, double ret, double ut) {
+    FILE *fp = std::fopen(path.c_str(), "w+");
+    if (!fp) { set_error("cannot open " + path); return CUDNS_EINVAL; }
+    std::fprintf(fp, "Reynolds number based on utau %lf with utau %lf\n", ret, ut);
+    static const char *legend[] = {"1)  y", "2)  rho", "3)  uFavre", "4)  vFavre", "5)  wFavre", "6)  u", "7)  v", "8)  w", "9)  eTotal", "10) hFavre",
+                                   "11) h", "12) Temperature", "13) Pressure", "13) visc"};
+    for (const char *l : legend) std::fprintf(fp, "%s\n", l);
+    for (int i = 0; i < 147; i++) std::fputc('-', fp);
+    std::fputc('\n', fp);
+    for (int i = 0; i < n; i++) {
+        std::fprintf(fp, "%le", x[i]);
+        for (int m = 0; m < 13; m++) std::fprintf(fp, "\t%le", q[(size_t)m * stride + i]);
+        std::fputc('\n', fp);
+    }
+    if (std::fclose(fp) != 0) { set_error("write error " + path); return CUDNS_EINVAL; }
+    return CUDNS_OK;
+}
+int cudns_stats_write(const char *outdir, int mx, const double *x, const double *mean, const double *fluc, const double *bulk, double retau, double utau) {
+    if (!x || !mean || !fluc || !bulk || mx < 1) { set_error("cudns_stats_write: bad argument"); return CUDNS_EINVAL; }
+    const std::string d = outdir && *outdir ? std::string(outdir) + "/" : std::string();
+    int rc = write_stats_file(d + "mean.txt", mx, x, mean, mx, retau, utau); if (rc) return rc;
+    rc = write_stats_file(d + "fluc.txt", mx, x, fluc, mx, retau, utau); if (rc) return rc;
+    return write_stats_file(d + "bulk.txt", 1, x, bulk, 1, retau, utau);
+}
+
 }  // extern "C"

@@ -119,6 +119,136 @@ void launch_retau(const KConst &kc, const double *q, double *partial, double *ou
 }
 
 // ---------------------------------------------------------------------------------------------
+// post-processing statistics on the device (postproc/post.cpp:126-326: the reference reads every saved field back to the host and
+// loops there, twice).  13 quantities per point in the column order of Variables::printFile (post.cpp:61-86):
+// rho, rho u, rho v, rho w, u, v, w, rho E, rho h, h, T, p, mu (the Favre rows hold rho-weighted sums until the division).
+// PASS 0: acc[13][mx] += scale * sum over this slab's (j,k) rows of q        (addMean, post.cpp:225-257)
+// PASS 1: acc[13][mx] += scale * sum of (q' - mean)^2, q' = u,v,w,h in the Favre rows   (addFluc, post.cpp:201-223)
+// Deterministic: block partials [POST_NB][13][mx], combined in a fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int POST_NB = 64, POST_NQ = 13;
+__device__ __forceinline__ void post_point(const KConst &c, const double *__restrict__ q, size_t g, double (&o)[POST_NQ]) {
+    const Layout &L = c.L;
+    const double r = q[g], u = q[L.vol + g], v = q[2 * L.vol + g], w = q[3 * L.vol + g], e = q[4 * L.vol + g];
+    const double invrho = 1.0 / r;                                              // calcState, post.cpp:259-278
+    const double en = e * invrho - 0.5 * (u * u + v * v + w * w);
+    const double t = c.cvInv * en, p = r * c.Rgas * t, h = (e + p) * invrho, m = visc_of(c, t);
+    o[0] = r; o[1] = r * u; o[2] = r * v; o[3] = r * w; o[4] = u; o[5] = v; o[6] = w; o[7] = e; o[8] = r * h; o[9] = h; o[10] = t; o[11] = p; o[12] = m;
+}
+template <int PASS>
+__global__ void __launch_bounds__(256) post_partial_kernel(KConst c, const double *__restrict__ q, const double *__restrict__ mean,
+                                                           double *__restrict__ partial) {
+    __shared__ double red[8][POST_NQ][32];
+    const Layout &L = c.L;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + tx, ic = min(i, L.mx - 1);
+    const long rows = (long)L.my * L.mz;
+    double m[POST_NQ], a[POST_NQ];
+#pragma unroll
+    for (int n = 0; n < POST_NQ; n++) { a[n] = 0.0; m[n] = PASS == 1 ? mean[n * L.mx + ic] : 0.0; }
+    for (long r = (long)blockIdx.y * 8 + ty; r < rows; r += (long)POST_NB * 8) {
+        const int j = (int)(r % L.my), k = (int)(r / L.my);
+        double o[POST_NQ];
+        post_point(c, q, L.idx(ic, j, k), o);
+        if (PASS == 1) { o[1] = o[4]; o[2] = o[5]; o[3] = o[6]; o[8] = o[9]; }
+#pragma unroll
+        for (int n = 0; n < POST_NQ; n++) a[n] += PASS == 0 ? o[n] : (o[n] - m[n]) * (o[n] - m[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < POST_NQ; n++) red[ty][n][tx] = a[n];
+    __syncthreads();
+    for (int n = ty; n < POST_NQ; n += 8) {
+        if (i < L.mx) {
+            double sum = 0.0;
+            for (int t = 0; t < 8; t++) sum += red[t][n][tx];
+            partial[((size_t)blockIdx.y * POST_NQ + n) * L.mx + i] = sum;
+        }
+    }
+}
+__global__ void post_combine_kernel(int mx, const double *__restrict__ partial, double *__restrict__ acc, double scale) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= POST_NQ * mx) return;
+    double sum = 0.0;
+    for (int b = 0; b < POST_NB; b++) sum += partial[(size_t)b * POST_NQ * mx + n];
+    acc[n] += sum * scale;
+}
+// calcRet (post.cpp:280-326) of one snapshot: per (j,k) the mean of |dw/dx| at the first two points next to either wall, advective
+// coefficients on the anti-mirrored w, wall density from the mean wall pressure (T_wall = 1); ret2[0] += Re_tau, ret2[1] += u_tau
+// (this slab's share of the mean over all rows).  partial[2][POST_NB]
+__global__ void __launch_bounds__(256) post_ret_partial_kernel(KConst c, const double *__restrict__ q, double host_dx, double *__restrict__ partial) {
+    __shared__ double red[2][256];
+    const Layout &L = c.L;
+    const long rows = (long)L.my * L.mz;
+    const int s = c.s, mx = L.mx;
+    const double muw = c.invRe;
+    double aR = 0.0, aU = 0.0;
+    for (long r = (long)blockIdx.x * 256 + threadIdx.x; r < rows; r += (long)POST_NB * 256) {
+        const int j = (int)(r % L.my), k = (int)(r / L.my);
+        const size_t g = L.idx(0, j, k);
+        const double *w = q + 3 * L.vol + g;
+        double o0[POST_NQ], o1[POST_NQ];
+        post_point(c, q, g, o0); post_point(c, q, g + mx - 1, o1);
+        const double rw = 0.5 * (o0[11] + o1[11]) / c.Rgas;
+        // ub[n], n = 0 .. mx+2s+1: ub[n] = w[n-s-1] inside, -w[s-n] below the lower wall, -w[2mx+s-n] above the upper one
+        auto ub = [&](int n) -> double { return n < 0 ? 0.0 : n <= s ? -w[s - n] : n <= mx + s ? w[n - s - 1] : -w[2 * mx + s - n]; };
+        auto dudx = [&](int jj) -> double {
+            double d = 0.0;
+            for (int it = 0; it < s; it++) d += -c.aF[s - it] * (ub(jj + it - s) - ub(jj - it + s)) / host_dx;       // coeffF[it] = -a_{s-it}
+            return d;
+        };
+        const double avg = (fabs(dudx(3)) + fabs(dudx(4)) + fabs(dudx(mx + s)) + fabs(dudx(mx + s + 1))) * 0.25 * c.xp[0];
+        const double ut = sqrt(muw * avg / rw);
+        aU += ut; aR += ut * rw / muw;
+    }
+    red[0][threadIdx.x] = aR; red[1][threadIdx.x] = aU;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) { red[0][threadIdx.x] += red[0][threadIdx.x + st]; red[1][threadIdx.x] += red[1][threadIdx.x + st]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[blockIdx.x] = red[0][0]; partial[POST_NB + blockIdx.x] = red[1][0]; }
+}
+__global__ void post_ret_combine_kernel(const double *partial, double *ret2, double scale) {
+    for (int n = 0; n < 2; n++) {
+        double sum = 0.0;
+        for (int b = 0; b < POST_NB; b++) sum += partial[n * POST_NB + b];
+        ret2[n] += sum * scale;
+    }
+}
+// after the last snapshot (and the cross-rank sum): volume averages from the un-divided profiles (addMean with N = 1: weight
+// dxv[i]/Lx), averages of Re_tau, u_tau over the snapshots, Favre division of rows 1-3 and 8 (post.cpp:180-187)
+__global__ void post_finish_mean_kernel(KConst c, double *mean, double *bulk, double *ret2, double inv_files) {
+    const int mx = c.L.mx;
+    const int n = threadIdx.x;
+    if (n < POST_NQ) {
+        double sum = 0.0;
+        for (int i = 0; i < mx; i++) sum += mean[n * mx + i] * c.dxv[i] / c.Lx;
+        bulk[n] = sum;
+    }
+    if (n == POST_NQ) { ret2[0] *= inv_files; ret2[1] *= inv_files; }
+    __syncthreads();
+    if (n == 0) { bulk[1] /= bulk[0]; bulk[2] /= bulk[0]; bulk[3] /= bulk[0]; bulk[8] /= bulk[0]; }
+    for (int i = n; i < mx; i += blockDim.x) {
+        const double r = mean[i];
+        mean[mx + i] /= r; mean[2 * mx + i] /= r; mean[3 * mx + i] /= r; mean[8 * mx + i] /= r;
+    }
+}
+int post_partial_doubles(const KConst &kc) { return POST_NB * POST_NQ * kc.L.mx; }
+void launch_post_accumulate(const KConst &kc, const double *q, const double *mean, double *partial, double *acc, double scale, int pass, cudaStream_t st) {
+    dim3 grid((kc.L.mx + 31) / 32, POST_NB);
+    if (pass == 0) post_partial_kernel<0><<<grid, 256, 0, st>>>(kc, q, mean, partial);
+    else post_partial_kernel<1><<<grid, 256, 0, st>>>(kc, q, mean, partial);
+    post_combine_kernel<<<(POST_NQ * kc.L.mx + 127) / 128, 128, 0, st>>>(kc.L.mx, partial, acc, scale);
+}
+void launch_post_ret(const KConst &kc, const double *q, double host_dx, double *partial, double *ret2, double scale, cudaStream_t st) {
+    post_ret_partial_kernel<<<POST_NB, 256, 0, st>>>(kc, q, host_dx, partial);
+    post_ret_combine_kernel<<<1, 1, 0, st>>>(partial, ret2, scale);
+}
+void launch_post_finish_mean(const KConst &kc, double *mean, double *bulk, double *ret2, double inv_files, cudaStream_t st) {
+    post_finish_mean_kernel<<<1, 128, 0, st>>>(kc, mean, bulk, ret2, inv_files);
+}
+
+// ---------------------------------------------------------------------------------------------
 // ghost handling, staging copies
 // ---------------------------------------------------------------------------------------------
 // periodic x/y images for nfields padded fields, all local planes incl. z ghosts (used by set_state)
@@ -315,6 +445,54 @@ constexpr int BULK_NB = 148 * 4;
 int bulk_scratch_doubles() { return 4 * BULK_NB + 1; }
 void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, double *scratch, cudaStream_t st) {
     bulk_reduce_kernel<<<BULK_NB, 256, 0, st>>>(kc, q, out4, scratch, (unsigned int *)(scratch + 4 * BULK_NB));
+}
+
+// Mean square vorticity <w.w> of a periodic box: volume average (weights of calcBulk's <u.u>) of |curl u|^2 with the viscous-order
+// first differences of derVelX/Y/Z (calc_stress.cu:20-86) read straight from the ghost-cell state.  Not a reference quantity -- the
+// reference never writes par2 without forcing (calc_stress.cu:191-197), so its Taylor-Green runs have no dissipation history; this
+// is the one libcudns offers (epsilon = <w.w>/Re in the incompressible limit).  Same deterministic two-level sum as the bulk kernel;
+// it runs every checkBulk steps, not per stage (3 of 8 state fields read once: ~0.1 % of the step loop at checkBulk = 10).
+__global__ void __launch_bounds__(256) enstrophy_reduce_kernel(KConst c, const double *__restrict__ q, double *out, double *partial, unsigned int *counter) {
+    const Layout &L = c.L;
+    const int nrows = L.my * L.mz;
+    const ptrdiff_t sy = L.px, sz = (ptrdiff_t)L.plane;
+    double s0 = 0;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int j = row % L.my, k = row / L.my;
+        const double *pu = q + L.vol + L.idx(0, j, k), *pv = pu + L.vol, *pw = pv + L.vol;
+        for (int i = threadIdx.x; i < L.mx; i += blockDim.x) {
+            double uy = 0, uz = 0, vx = 0, vz = 0, wx = 0, wy = 0;
+            for (int l = 1; l <= c.v; l++) {
+                const double cx = c.c1[0][l], cy = c.c1[1][l], cz = c.c1[2][l];
+                vx = fma(cx, pv[i + l] - pv[i - l], vx); wx = fma(cx, pw[i + l] - pw[i - l], wx);
+                uy = fma(cy, pu[i + l * sy] - pu[i - l * sy], uy); wy = fma(cy, pw[i + l * sy] - pw[i - l * sy], wy);
+                uz = fma(cz, pu[i + l * sz] - pu[i - l * sz], uz); vz = fma(cz, pv[i + l * sz] - pv[i - l * sz], vz);
+            }
+            if (c.nonUniformX) { vx *= c.xp[i]; wx *= c.xp[i]; }
+            const double ox = wy - vz, oy = uz - wx, oz = vx - uy;
+            s0 += (ox * ox + oy * oy + oz * oz) * c.dxv[i] / c.d1[1] / c.d1[2] / c.Lx / c.Ly / c.Lz;
+        }
+    }
+    __shared__ double sh[8];
+    s0 = warp_sum(s0);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s0;
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        double a = 0; for (int q8 = 0; q8 < 8; q8++) a += sh[q8];
+        partial[blockIdx.x] = a;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        double a = 0; for (unsigned int b = 0; b < gridDim.x; b++) a += partial[b];
+        *out = a; *counter = 0;
+    }
+}
+// scratch: the solver's bulk scratch (bulk_scratch_doubles(): the first BULK_NB partials and the counter are used)
+void launch_enstrophy_reduce(const KConst &kc, const double *q, double *out, double *scratch, cudaStream_t st) {
+    enstrophy_reduce_kernel<<<BULK_NB, 256, 0, st>>>(kc, q, out, scratch, (unsigned int *)(scratch + 4 * BULK_NB));
 }
 
 // tiny scalar kernels (deviceSumOne, deviceAdvanceTime, deviceCalcPress, ... cuda_math.cu:17-52, calc_stress.cu:12-18)

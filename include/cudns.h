@@ -63,7 +63,9 @@ typedef struct cudns_params {
     int nranks;                /* number of z-slabs (1 = single GPU)                  */
     int rank;                  /* this process' slab index: k in [rank*mz/nranks, (rank+1)*mz/nranks) */
     int device;                /* CUDA device ordinal for this rank (setDevice, cuda_utils.cu:815) */
-    int reserved[5];
+    int par2_enstrophy;        /* extension, default 0 = reference behaviour (calc_stress.cu:191-197 never writes par2 without forcing):
+                                * 1 makes cudns_advance record the mean square vorticity <w.w> of an unforced periodic box in par2 */
+    int reserved[4];
 } cudns_params;
 
 typedef struct cudns_solver *cudns_handle;
@@ -138,6 +140,10 @@ int cudns_calc_rhs(cudns_handle h, double *rhs_r, double *rhs_u, double *rhs_v, 
 int cudns_calc_dt(cudns_handle h, double *dt);
 /* calcBulk (calc_stress.cu:162-201) + allReduceSum (comm.cpp:326) */
 int cudns_calc_bulk(cudns_handle h, double *par1, double *par2);
+/* mean square vorticity <w.w> = volume average (the weights of calcBulk's <u.u>) of |curl u|^2 with the viscous-order differences of
+ * derVelX/Y/Z (calc_stress.cu:20-86), summed over the slabs: the dissipation measure of a Taylor-Green run (epsilon = <w.w>/Re in
+ * the incompressible limit).  Extension -- the reference has no counterpart; periodic boxes only (CUDNS_EUNSUPPORTED otherwise). */
+int cudns_calc_enstrophy(cudns_handle h, double *enstrophy);
 /* device scalars dtC, dpdz (cuda_utils.cu:65-75), accumulated time (cuda_main.cu:117-119) */
 int cudns_get_scalars(cudns_handle h, double *dt, double *dpdz, double *time);
 /* fix dt (tests): fixed != 0 disables the CFL refresh inside cudns_advance */
@@ -210,6 +216,27 @@ int cudns_read_fields(cudns_handle h, const char *dir, int timestep);
 int cudns_calc_profiles(cudns_handle h, double *prof);
 /* printRes (init.cpp:210-256): average friction Reynolds number of the wall at i = 0 */
 int cudns_calc_retau(cudns_handle h, double *retau);
+
+/* ---- post-processing statistics: postproc/post.cpp as device reductions ---------------------------------
+ * The reference's tool reads fields/<c>.<first..last>.bin back to the host twice and loops there: Reynolds and Favre means per
+ * wall-normal index (addMean, post.cpp:225-257), volume averages (the same with N = 1), friction Reynolds number and velocity
+ * (calcRet, :280-326), then the mean squares about those means (addFluc, :201-223).  Here every snapshot is reduced on the device
+ * from the solver's current state -- live (between cudns_advance calls) or re-read (cudns_read_fields):
+ *     cudns_stats_begin(h, n);  n x { state; cudns_stats_add_mean(h); }  cudns_stats_finish_mean(h);
+ *     n x { the same states again; cudns_stats_add_fluc(h); }  cudns_stats_get(h, ...);
+ * mean / fluc are [13][mx], bulk is [13], in the column order of Variables::printFile (post.cpp:61-86):
+ * rho, uFavre, vFavre, wFavre, u, v, w, eTotal, hFavre, h, T, p, mu.  Slabs add up through the all-reduce callback (every rank gets the
+ * result).  Re_tau / u_tau are 0 for periodic-x set-ups and for stencilSize = 4 (the reference's index arithmetic, post.cpp:303-306,
+ * leaves its array there). */
+int cudns_stats_begin(cudns_handle h, int nsnapshots);
+int cudns_stats_add_mean(cudns_handle h);
+int cudns_stats_finish_mean(cudns_handle h);
+int cudns_stats_add_fluc(cudns_handle h);
+int cudns_stats_get(cudns_handle h, double *mean, double *fluc, double *bulk, double *retau, double *utau);
+/* Variables::printFile (post.cpp:61-86): mean.txt, fluc.txt, bulk.txt in outdir (NULL or "": the working directory); host only */
+int cudns_stats_write(const char *outdir, int mx, const double *x, const double *mean, const double *fluc, const double *bulk, double retau, double utau);
+/* main() of post.cpp (:126-199): both passes over fields/<c>.<first..last>.bin under dir, then the three files (written by rank 0) */
+int cudns_postprocess(cudns_handle h, const char *dir, int first, int last, const double *x, const char *outdir);
 
 #ifdef __cplusplus
 }

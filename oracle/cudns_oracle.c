@@ -739,6 +739,24 @@ void ora_calc_bulk(ora_solver *S, double *par1, double *par2) {
     }
 }
 
+/* Mean square vorticity <w.w> (volume average with the weights of calcBulk's <u.u>) from the viscous-order velocity gradients of
+ * derVelX/Y/Z (calc_stress.cu:20-86).  NOT a reference quantity: the reference never writes par2 without forcing (quirk Q6), so a
+ * Taylor-Green run has no dissipation history; this is the definition libcudns offers for it (epsilon = <w.w>/Re for the
+ * incompressible limit), restated here so that the device reduction has a checker. */
+double ora_calc_enstrophy(ora_solver *S) {
+    derVel(S);
+    int mx = S->mx; double sum = 0.0;
+    const double Lx = S->P.Lx, Ly = S->P.Ly, Lz = S->P.Lz;
+    #pragma omp parallel for reduction(+:sum) schedule(static)
+    for (long g = 0; g < (long)S->N; g++) {
+        int i = (int)(g % mx);
+        /* gij[3*d + m] = d u_m / d x_d */
+        double wx = S->gij[3*1+2][g] - S->gij[3*2+1][g], wy = S->gij[3*2+0][g] - S->gij[3*0+2][g], wz = S->gij[3*0+1][g] - S->gij[3*1+0][g];
+        sum += (wx*wx + wy*wy + wz*wz)*S->dxv[i]/S->d_dy/S->d_dz/Lx/Ly/Lz;
+    }
+    return sum;
+}
+
 /* calcAvgChan init.cpp:150-208: y-z averages per wall-normal index i.  prof[0..4][i] = <rho>, <rho u>/<rho>, <rho v>/<rho>,
  * <rho w>/<rho>, <rho E>; prof[5..9][i] = mean squares of (rho, u, v, w, rho E) about those means (prof.txt columns 2..11) */
 void ora_calc_profiles(ora_solver *S, double *prof) {
@@ -792,6 +810,99 @@ double ora_calc_retau(ora_solver *S) {
             Ret += ut*S->r[g0]/muw;
         }
     return Ret/my/mz;
+}
+
+/* ------------------------------------------------------------------ post-processing statistics (postproc/post.cpp)
+ * Restatement of the reference's post-processing tool: Reynolds / Favre means and the mean squares about them per wall-normal
+ * index, volume averages, friction Reynolds number and friction velocity, over a series of saved fields (post.cpp:126-326).
+ * Pinned by running the reference's own tool (oracle/refbuild/build_ref_post.sh -> oracle/_ref/post_*) on the same fields/:
+ * tests/golden/ref_post_*.npz, tests/test_post.py.  Row order of the 13 quantities = column order of Variables::printFile
+ * (post.cpp:61-86): rho, uFavre, vFavre, wFavre, u, v, w, eTotal, hFavre, h, T, p, mu. */
+enum { PQ_R = 0, PQ_UF, PQ_VF, PQ_WF, PQ_U, PQ_V, PQ_W, PQ_E, PQ_HF, PQ_H, PQ_T, PQ_P, PQ_M, PQ_N };
+struct ora_post {
+    int mx, nfiles;
+    double denom;
+    double *mean, *fluc;        /* [13][mx] */
+    double bulk[PQ_N];
+    double Ret, ut;
+};
+ora_post *ora_post_create(ora_solver *S, int nfiles) {
+    ora_post *P = (ora_post*)calloc(1, sizeof(ora_post));
+    P->mx = S->mx; P->nfiles = nfiles;
+    P->denom = (double)(nfiles*S->my*S->mz);               /* post.cpp:166 (int arithmetic there) */
+    P->mean = (double*)calloc((size_t)PQ_N*S->mx, sizeof(double));
+    P->fluc = (double*)calloc((size_t)PQ_N*S->mx, sizeof(double));
+    return P;
+}
+void ora_post_destroy(ora_post *P) { if (P) { free(P->mean); free(P->fluc); free(P); } }
+/* calcState post.cpp:259-278 at one point */
+static void post_state(const ora_solver *S, size_t g, double q[PQ_N]) {
+    const double cvInv = (S->P.gam - 1.0)/S->Rgas;
+    const double r = S->r[g], u = S->u[g], v = S->v_[g], w = S->w[g], e = S->e[g];
+    const double invrho = 1.0/r;
+    const double en = e*invrho - 0.5*(u*u + v*v + w*w);
+    const double t = cvInv*en, p = r*S->Rgas*t, h = (e + p)*invrho, m = pow(t, S->P.viscexp)/S->P.Re;
+    q[PQ_R] = r; q[PQ_UF] = r*u; q[PQ_VF] = r*v; q[PQ_WF] = r*w; q[PQ_U] = u; q[PQ_V] = v; q[PQ_W] = w; q[PQ_E] = e;
+    q[PQ_HF] = r*h; q[PQ_H] = h; q[PQ_T] = t; q[PQ_P] = p; q[PQ_M] = m;
+}
+/* addMean (post.cpp:225-257) for `mean` and `bulk`, calcRet (:280-326), of the solver's current state */
+void ora_post_add_mean(ora_post *P, ora_solver *S) {
+    const int mx = S->mx, my = S->my, mz = S->mz, s = S->s;
+    for (int i = 0; i < mx; i++) {
+        const double denom2 = S->P.Lx/S->dxv[i]*P->denom;
+        for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) {
+            double q[PQ_N]; post_state(S, (size_t)i + (size_t)mx*(j + (size_t)my*k), q);
+            for (int n = 0; n < PQ_N; n++) { P->mean[(size_t)n*mx + i] += q[n]/P->denom; P->bulk[n] += q[n]/denom2; }
+        }
+    }
+    double ut = 0.0, Ret = 0.0;
+    double *ub = (double*)malloc(sizeof(double)*(mx + 2*s + 2)), *dudx = (double*)malloc(sizeof(double)*(mx + 2*s + 2));
+    for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) {
+        const size_t row = (size_t)mx*(j + (size_t)my*k);
+        double q0[PQ_N], q1[PQ_N]; post_state(S, row, q0); post_state(S, row + mx - 1, q1);
+        const double rw = 0.5*(q0[PQ_P] + q1[PQ_P])/S->Rgas, muw = 1.0/S->P.Re;
+        for (int i = 0; i < mx; i++) ub[i+s+1] = S->w[row + i];
+        for (int i = 0; i < s+1; i++) { ub[i] = -S->w[row + s - i]; ub[mx+s+1+i] = -S->w[row + mx - i - 1]; }
+        for (int jj = 3; jj < mx+s+2; jj++) {
+            dudx[jj] = 0;
+            for (int i = 0; i < s; i++) {
+                /* s = 4: the reference reads ub[-1] at jj = 3 (post.cpp:303-306, outside its array); taken as 0 here */
+                const int a = jj+i-s, b = jj-i+s;
+                dudx[jj] += S->cF[i]*((a >= 0 ? ub[a] : 0.0) - ub[b])/S->dx;
+            }
+        }
+        double dudxavg = fabs(dudx[3]) + fabs(dudx[4]) + fabs(dudx[mx+s]) + fabs(dudx[mx+s+1]);
+        dudxavg = dudxavg*0.25*S->xp[0];
+        const double uttemp = sqrt(muw*dudxavg/rw);
+        ut += uttemp; Ret += uttemp*rw/muw;
+    }
+    free(ub); free(dudx);
+    P->Ret += Ret/my/mz; P->ut += ut/my/mz;
+}
+/* after the last file: post.cpp:180-187 (averages over the files, Favre division) */
+void ora_post_finish_mean(ora_post *P) {
+    P->Ret /= P->nfiles; P->ut /= P->nfiles;
+    for (int i = 0; i < P->mx; i++) {
+        const double r = P->mean[(size_t)PQ_R*P->mx + i];
+        P->mean[(size_t)PQ_UF*P->mx + i] /= r; P->mean[(size_t)PQ_VF*P->mx + i] /= r; P->mean[(size_t)PQ_WF*P->mx + i] /= r;
+        P->mean[(size_t)PQ_HF*P->mx + i] /= r;
+    }
+    P->bulk[PQ_UF] /= P->bulk[PQ_R]; P->bulk[PQ_VF] /= P->bulk[PQ_R]; P->bulk[PQ_WF] /= P->bulk[PQ_R]; P->bulk[PQ_HF] /= P->bulk[PQ_R];
+}
+/* addFluc (post.cpp:201-223): mean squares about the Reynolds means (r,u,v,w,e,h,t,p,m) and of u,v,w,h about the Favre means */
+void ora_post_add_fluc(ora_post *P, ora_solver *S) {
+    const int mx = S->mx, my = S->my, mz = S->mz;
+    for (int i = 0; i < mx; i++) for (int k = 0; k < mz; k++) for (int j = 0; j < my; j++) {
+        double q[PQ_N]; post_state(S, (size_t)i + (size_t)mx*(j + (size_t)my*k), q);
+        q[PQ_UF] = q[PQ_U]; q[PQ_VF] = q[PQ_V]; q[PQ_WF] = q[PQ_W]; q[PQ_HF] = q[PQ_H];
+        for (int n = 0; n < PQ_N; n++) { const double d = q[n] - P->mean[(size_t)n*mx + i]; P->fluc[(size_t)n*mx + i] += d*d/P->denom; }
+    }
+}
+void ora_post_get(const ora_post *P, double *mean, double *fluc, double *bulk, double *Ret, double *ut) {
+    if (mean) memcpy(mean, P->mean, sizeof(double)*PQ_N*P->mx);
+    if (fluc) memcpy(fluc, P->fluc, sizeof(double)*PQ_N*P->mx);
+    if (bulk) memcpy(bulk, P->bulk, sizeof(double)*PQ_N);
+    if (Ret) *Ret = P->Ret; if (ut) *ut = P->ut;
 }
 
 /* calcTimeStepPressGrad cuda_main.cu:249-265, calcPressureGrad calc_stress.cu:98-120 */

@@ -117,8 +117,20 @@ void ora_calc_rhs(ora_solver *s, double *rhs[5]);
 double ora_calc_dt(ora_solver *s);
 /* calcBulk (calc_stress.cu:162-201) */
 void ora_calc_bulk(ora_solver *s, double *par1, double *par2);
+/* mean square vorticity at viscous order (libcudns's par2 of the unforced runs; not a reference quantity) */
+double ora_calc_enstrophy(ora_solver *s);
 /* calcAvgChan init.cpp:150-208: prof[10][mx] = y-z means (rho, Favre u,v,w, rho E) and mean squares about them */
 void ora_calc_profiles(ora_solver *s, double *prof);
+/* postproc/post.cpp: statistics over a series of saved fields.  create(nfiles); for every file: load it into the solver
+ * (ora state arrays + ora_copy_field_in) and add_mean; finish_mean; for every file again: add_fluc; get.  mean/fluc are [13][mx]
+ * in the column order of Variables::printFile (rho uF vF wF u v w e hF h T p mu), bulk[13] the volume averages */
+typedef struct ora_post ora_post;
+ora_post *ora_post_create(ora_solver *s, int nfiles);
+void ora_post_destroy(ora_post *p);
+void ora_post_add_mean(ora_post *p, ora_solver *s);
+void ora_post_finish_mean(ora_post *p);
+void ora_post_add_fluc(ora_post *p, ora_solver *s);
+void ora_post_get(const ora_post *p, double *mean, double *fluc, double *bulk, double *Ret, double *ut);
 /* printRes init.cpp:210-256: average friction Reynolds number at the wall i = 0 */
 double ora_calc_retau(ora_solver *s);
 

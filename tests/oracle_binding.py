@@ -69,9 +69,16 @@ def lib():
         L.ora_calc_rhs.argtypes = [C.c_void_p, C.POINTER(dp)]
         L.ora_calc_dt.argtypes = [C.c_void_p]; L.ora_calc_dt.restype = C.c_double
         L.ora_calc_bulk.argtypes = [C.c_void_p, dp, dp]
+        L.ora_calc_enstrophy.argtypes = [C.c_void_p]; L.ora_calc_enstrophy.restype = C.c_double
         L.ora_calc_profiles.argtypes = [C.c_void_p, dp]
         L.ora_calc_retau.argtypes = [C.c_void_p]; L.ora_calc_retau.restype = C.c_double
         L.ora_run.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+        L.ora_post_create.argtypes = [C.c_void_p, C.c_int]; L.ora_post_create.restype = C.c_void_p
+        L.ora_post_destroy.argtypes = [C.c_void_p]
+        L.ora_post_add_mean.argtypes = [C.c_void_p, C.c_void_p]
+        L.ora_post_finish_mean.argtypes = [C.c_void_p]
+        L.ora_post_add_fluc.argtypes = [C.c_void_p, C.c_void_p]
+        L.ora_post_get.argtypes = [C.c_void_p, dp, dp, dp, dp, dp]
         for name in ("ora_get_dt", "ora_get_dpdz", "ora_get_time"):
             f = getattr(L, name); f.argtypes = [C.c_void_p]; f.restype = C.c_double
         L.ora_set_dt.argtypes = [C.c_void_p, C.c_double]
@@ -218,6 +225,22 @@ class Oracle:
         return out
 
     def retau(self): return self.L.ora_calc_retau(self.h)
+
+    def enstrophy(self): return self.L.ora_calc_enstrophy(self.h)
+
+    def post_stats(self, snapshots):
+        """postproc/post.cpp over a list of states: dict(mean[13][mx], fluc[13][mx], bulk[13], Ret, ut)"""
+        P = self.L.ora_post_create(self.h, len(snapshots))
+        for st in snapshots:
+            self.set_state(st); self.L.ora_post_add_mean(P, self.h)
+        self.L.ora_post_finish_mean(P)
+        for st in snapshots:
+            self.set_state(st); self.L.ora_post_add_fluc(P, self.h)
+        mean = np.zeros((13, self.p.mx)); fluc = np.zeros((13, self.p.mx)); bulk = np.zeros(13)
+        a = C.c_double(0.0); b = C.c_double(0.0)
+        self.L.ora_post_get(P, _dp(mean), _dp(fluc), _dp(bulk), C.byref(a), C.byref(b))
+        self.L.ora_post_destroy(P)
+        return dict(mean=mean, fluc=fluc, bulk=bulk, Ret=a.value, ut=b.value)
 
     def run(self, nsteps):
         t = np.zeros(nsteps); p1 = np.full(nsteps, np.nan); p2 = np.full(nsteps, np.nan)
