@@ -99,10 +99,11 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def scheme_params(cd, n, scheme):
+def scheme_params(cd, n, scheme, prec=0):
     p = cd.params_tgv(n, 4)
     p.lowStorage = 1 if scheme == "ls3" else 0
     p.rk4 = 1 if scheme == "rk4" else 0
+    p.precision = prec                   # 0: double (the headline), 1: float (`myprec float`, globals.h:5-6)
     return p
 
 
@@ -128,10 +129,10 @@ def tgv_slab(out, grid, p, k0, mzl):
         e[a:b] = press / (p.gam - 1.0) + 0.5 * r[a:b] * (u[a:b] * u[a:b] + v[a:b] * v[a:b])
 
 
-def make_config(n, scheme, world):
+def make_config(n, scheme, world, prec=0):
     """the `config` object of the bench line -- built by one function so that both arms print the same"""
-    npts = float(n) ** 3
-    return {"workload": "tgv%d_s4v4_fp64_%s" % (n, scheme), "grid": [n, n, n], "scheme": scheme, "stages_per_step": STAGES[scheme],
+    npts = float(n) ** 3 * (0.5 if prec else 1.0)
+    return {"workload": "tgv%d_s4v4_%s_%s" % (n, "fp32" if prec else "fp64", scheme), "grid": [n, n, n], "scheme": scheme, "stages_per_step": STAGES[scheme],
             "stencilSize": 4, "stencilVisc": 4, "decomposition": "z-slabs x%d" % world,
             "halo": ("peer-memory stores from the stage kernel over NVLink (CUDA IPC) + device-side epoch flags"
                      if world > 1 else "periodic z wrap stored by the stage kernel"),
@@ -283,11 +284,11 @@ def main():
     tgv_slab(host, grid, p0, rank * mzl, mzl)
     views = [host[f] for f in range(5)]
 
-    def measure(scheme, steps, warmup, with_clocks):
+    def measure(scheme, steps, warmup, with_clocks, prec=0):
         """one solver of `scheme`: K timed steps between CUDA events on the solver's stream (max over ranks), then the same K steps
         again with CUDA events around every stage (kernel times under the sustained load of the step loop), then isolated launches"""
         stages = STAGES[scheme]
-        p = scheme_params(cd, n, scheme)
+        p = scheme_params(cd, n, scheme, prec)
         p.nranks = world; p.rank = rank; p.device = local
         sol = cd.Solver(p, grid)
         if world > 1:
@@ -325,21 +326,22 @@ def main():
             clocks["covers"] = "timed region + %d steps of the same workload with per-stage events" % extra
         prof = sol.profile_stage(5)
         value = npts * stages * steps / (ms * 1e-3) / 1e6          # Mpts*stage/s, whole job
-        alg = ALG_BYTES[scheme] * npts / world                      # algorithmic bytes per launch of the stage kernel on one rank
+        bpp = ALG_BYTES[scheme] * (0.5 if prec else 1.0)           # algorithmic bytes per point-stage (80 B in FP32)
+        alg = bpp * npts / world                                    # algorithmic bytes per launch of the stage kernel on one rank
         k_sust = max_over_ranks(sust["rhs_stage_ms"]); k_burst = max_over_ranks(prof["rhs_stage_ms"])
-        kernel = ("duo::stage_kernel<4,4> (two points per thread)" if (scheme != "ls3" or os.environ.get("CUDNS_DUO") == "1")
+        kernel = ("duo::stage_kernel<4,4> (two points per thread)" if (scheme != "ls3" or prec or os.environ.get("CUDNS_DUO") == "1")
                   else "fast::stage_kernel<4,4,8>") + ": fused RHS + RK stage update + H,T of the new state + halo stores"
         roofline = {"bound": "hbm", "kernel": kernel, "achieved": alg / (k_sust * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind,
                     "unit": "GB/s", "frac": alg / (k_sust * 1e-3) / 1e9 / peak,
-                    "traffic": ncu_traffic("rhs_stage_%d_%s" % (n, scheme)) if world == 1 else None,
-                    "alg_bytes_per_launch": alg, "alg_bytes_per_point": ALG_BYTES[scheme],
+                    "traffic": ncu_traffic("rhs_stage_%d_%s%s" % (n, scheme, "_f32" if prec else "")) if world == 1 else None,
+                    "alg_bytes_per_launch": alg, "alg_bytes_per_point": bpp,
                     "kernel_ms": k_sust, "kernel_ms_how": "mean over %d launches inside the step loop (CUDA events around every stage, sustained clocks)" % sust["stages"],
                     "kernel_ms_burst": k_burst, "frac_burst": alg / (k_burst * 1e-3) / 1e9 / peak,
                     "kernel_ms_burst_how": "5 isolated launches of the scheme's most frequent stage shape (cudns_profile_stage)",
                     "theta_ms": max_over_ranks(sust["theta_ms"]), "theta_ms_burst": prof["theta_ms"], "handshake_ms": max_over_ranks(sust["halo_ms"]),
                     # whole step (dilatation pass, reductions, hand-shake included), per GPU against one GPU's peak
-                    "whole_step_achieved": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world,
-                    "whole_step_frac": ALG_BYTES[scheme] * value * 1e6 / 1e9 / world / peak}
+                    "whole_step_achieved": bpp * value * 1e6 / 1e9 / world,
+                    "whole_step_frac": bpp * value * 1e6 / 1e9 / world / peak}
         return sol, {"value": value, "ms_per_step": ms / steps, "launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
                      "roofline": roofline, "clocks": clocks}
 
@@ -374,7 +376,15 @@ def main():
         s4, r4 = measure("rk4", args.steps, args.warmup, False)
         s4.close()
         schemes = {"rk4": {"config": make_config(n, "rk4", world), "value": r4["value"], "unit": "Mpts*RK-stage/s", "ms_per_step": r4["ms_per_step"],
-                           "stages_per_step": 4, "roofline": r4["roofline"], "gpu_launches": r4["launches"]}}
+                           "stages_per_step": 4, "roofline": r4["roofline"], "gpu_launches": r4["launches"], "dtype": "f64"}}
+        # ---- single precision (`myprec float` of the reference, globals.h:5-6): the same step with the float copy of the device side,
+        # 80 algorithmic bytes per point-stage.  Not the headline (BASELINE names FP64); reported because it is the configuration in which
+        # the path is closest to its HBM roofline
+        s32, r32 = measure(scheme, args.steps, args.warmup, False, prec=1)
+        s32.close()
+        schemes["%s_fp32" % scheme] = {"config": make_config(n, scheme, world, 1), "value": r32["value"], "unit": "Mpts*RK-stage/s",
+                                       "ms_per_step": r32["ms_per_step"], "stages_per_step": stages, "roofline": r32["roofline"],
+                                       "gpu_launches": r32["launches"], "dtype": "f32"}
 
     cpu = None
     refgpu = None

@@ -61,7 +61,7 @@ class Params(C.Structure):
         ("amp1", C.c_double), ("amp2", C.c_double), ("omega1", C.c_double), ("omega2", C.c_double),
         ("quirk_q1", C.c_int), ("rk4", C.c_int),
         ("nranks", C.c_int), ("rank", C.c_int), ("device", C.c_int),
-        ("par2_enstrophy", C.c_int), ("reserved", C.c_int * 4),
+        ("par2_enstrophy", C.c_int), ("precision", C.c_int), ("reserved", C.c_int * 3),
     ]
 
 

@@ -13,12 +13,10 @@
 #include <thread>
 
 namespace cudns {
-const double *coeff_first(int s);
-const double *coeff_second(int s);
-int check_params(const cudns_params *p);
 void launch_dt_combine(double *dt, const double *conv, const double *visc, double cfl, cudaStream_t st);
 }
 using namespace cudns;
+static constexpr bool kF32 = sizeof(real) == 4;     // this translation unit is the single-precision copy (see cudns_internal.h)
 
 // inside cudns_create, once the solver object exists: a failing CUDA call must not leak it
 #define CKC(call)                                                                                    \
@@ -69,6 +67,7 @@ struct StageTimer {
 };
 
 struct cudns_solver {
+    int precision;               // FIRST member of both precisions' solver objects: 0 double, 1 float (abi_dispatch.cpp reads it)
     IoState *io;
     StageTimer *tm;
     cudns_params P;
@@ -76,18 +75,18 @@ struct cudns_solver {
     Layout L;
     size_t N;                    // local interior points
     cudaStream_t st;
-    double *block;               // ONE allocation: nstate padded 5-field buffers + the neighbour mailbox (a single IPC handle covers it)
+    real *block;               // ONE allocation: nstate padded 5-field buffers + the neighbour mailbox (a single IPC handle covers it)
     size_t block_doubles;        // state part of the block, in doubles; the mailbox (8 x u64) follows
-    double *state[3];            // padded 5-field buffers inside block
+    real *state[3];            // padded 5-field buffers inside block
     int nstate, cur;
     // peer-memory halo transport (cudns_halo_connect): the neighbours' blocks mapped into this process
-    double *peer_lo, *peer_hi;   // nullptr: not connected / no such neighbour
+    real *peer_lo, *peer_hi;   // nullptr: not connected / no such neighbour
     void *ipc_lo, *ipc_hi;       // what cudaIpcOpenMemHandle returned (to close), nullptr for same-process peers
     bool connected;
     unsigned long long epoch;    // stage counter of the hand-shake
-    double *theta;
-    double *R1, *R2;
-    double *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
+    real *theta;
+    real *R1, *R2;
+    real *d_xp, *d_cVSx, *d_dxv, *d_spx, *d_spz, *d_sref;
     double *d_scal;
     double *d_hist; int hist_cap;
     double *d_bulk;              // bulk_reduce_kernel scratch (block partials + completion counter), this solver's own
@@ -95,7 +94,7 @@ struct cudns_solver {
     double *d_prof;              // profile diagnostics scratch: partial[64][5][mx], mean[5][mx], var[5][mx], 1 scalar (lazy)
     double *d_post;              // post-processing statistics: partial[64][13][mx], mean[13][mx], fluc[13][mx], bulk[13], Re_tau, u_tau (lazy)
     int post_phase, post_files, post_added;   // 0 idle, 1 collecting means, 2 means final / collecting fluctuations, 3 fluctuations final
-    double *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
+    real *send_lo, *send_hi, *recv_lo, *recv_hi; size_t halo_doubles;
     bool have_state, fixed_dt, have_sponge;
     cudns_allreduce_fn allreduce; void *allreduce_user;
     cudns_exchange_fn exchange; void *exchange_user;
@@ -132,38 +131,44 @@ static encode_tiled_fn get_encode() {
     return fn;
 }
 // padded field(s) [nf][pz][py][px] of doubles -> descriptor with box bx x by x 1 (x nf)
-static int make_map(CUtensorMap *m, const Layout &L, double *base, int nf, int bx, int by) {
+static int make_map(CUtensorMap *m, const Layout &L, real *base, int nf, int bx, int by) {
     encode_tiled_fn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CUDNS_ECUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)L.px, (cuuint64_t)L.py, (cuuint64_t)L.pz, (cuuint64_t)nf};
-    cuuint64_t strides[3] = {(cuuint64_t)L.px * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.vol * 8};
+    cuuint64_t strides[3] = {(cuuint64_t)L.px * sizeof(real), (cuuint64_t)L.plane * sizeof(real), (cuuint64_t)L.vol * sizeof(real)};
     cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)nf};
     cuuint32_t es[4] = {1, 1, 1, 1};
     const int rank = nf > 1 ? 4 : 3;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, CUDNS_TMA_REAL, rank, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r)); return CUDNS_ECUDA; }
     return CUDNS_OK;
 }
 
 // unpadded register array [5][mz][my][mx] -> descriptor with box 32 x ty x 1 x 5
-static int make_rmap(CUtensorMap *m, const Layout &L, double *base, int ty) {
+static int make_rmap(CUtensorMap *m, const Layout &L, real *base, int ty) {
     encode_tiled_fn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return CUDNS_ECUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)L.mx, (cuuint64_t)L.my, (cuuint64_t)L.mz, 5};
-    cuuint64_t strides[3] = {(cuuint64_t)L.mx * 8, (cuuint64_t)L.mx * L.my * 8, (cuuint64_t)L.mx * L.my * L.mz * 8};
+    cuuint64_t strides[3] = {(cuuint64_t)L.mx * sizeof(real), (cuuint64_t)L.mx * L.my * sizeof(real), (cuuint64_t)L.mx * L.my * L.mz * sizeof(real)};
     cuuint32_t box[4] = {32, (cuuint32_t)ty, 1, 5};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, CUDNS_TMA_REAL, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (register array) failed with CUresult " + std::to_string((int)r)); return CUDNS_ECUDA; }
     return CUDNS_OK;
 }
 
-static int dmalloc(cudns_solver *S, double **p, size_t n) {
-    cudaError_t e = cudaMalloc((void **)p, n * sizeof(double));
+// host table (double) -> device table of the working precision (the cast of setGPUParameters, cuda_utils.cu:60-139)
+static cudaError_t upload(real *dst, const double *src, size_t n) {
+    std::vector<real> tmp(src, src + n);
+    return cudaMemcpy(dst, tmp.data(), n * sizeof(real), cudaMemcpyHostToDevice);
+}
+
+template <typename T> static int dmalloc(cudns_solver *S, T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return CUDNS_ENOMEM; }
-    S->bytes += n * sizeof(double);
+    S->bytes += n * sizeof(T);
     return CUDNS_OK;
 }
 
@@ -181,6 +186,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     cudns_solver *S = new cudns_solver();
     std::memset(S, 0, sizeof(*S));
     S->P = *p;
+    S->precision = kF32 ? 1 : 0;
     const int s = p->stencilSize, v = p->stencilVisc, mx = p->mx, my = p->my, mzl = p->mz / p->nranks;
     if (!p->periodicX) {
         int rem = mx % 32;
@@ -206,18 +212,23 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         // points each): CUDNS_DUO=1 forces the fifth generation there too, CUDNS_DUO=0 switches it off
         const char *de = getenv("CUDNS_DUO");
         const bool ls3 = p->lowStorage && !p->rk4;
-        const bool want = de ? std::string(de) != "0" : !ls3;
-        S->duo = S->fast && !fe && mx % 2 == 0 && want && (size_t)duo_smem_bytes(s) <= prop.sharedMemPerBlockOptin;
+        const bool want = kF32 || (de ? std::string(de) != "0" : !ls3);
+        S->duo = S->fast && (!fe || kF32) && mx % 2 == 0 && want && (size_t)duo_smem_bytes(s) <= prop.sharedMemPerBlockOptin;
+        if (kF32 && !S->duo) {
+            // `myprec float` (globals.h:5-6) is built for the set-ups the fifth-generation kernel serves
+            set_error("precision = 1 (float) needs periodicX = 1, nonUniformX = 0, boundaryLayer = 0, viscexp = 1 and an even mx");
+            cudns_destroy(S); return CUDNS_EUNSUPPORTED;
+        }
     }
     S->block_doubles = (size_t)S->nstate * S->nfb * L.vol;
     S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
     if ((rc = dmalloc(S, &S->block, S->block_doubles + 32))) { cudns_destroy(S); return rc; }
-    CKC(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->block, 0, (S->block_doubles + 32) * sizeof(real), S->st));
     for (int b = 0; b < S->nstate; b++) S->state[b] = S->block + (size_t)b * S->nfb * L.vol;
     if ((rc = dmalloc(S, &S->theta, L.vol))) { cudns_destroy(S); return rc; }
-    CKC(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->theta, 0, L.vol * sizeof(real), S->st));
     if ((rc = dmalloc(S, &S->R1, 5 * S->N))) { cudns_destroy(S); return rc; }
-    CKC(cudaMemsetAsync(S->R1, 0, 5 * S->N * sizeof(double), S->st));
+    CKC(cudaMemsetAsync(S->R1, 0, 5 * S->N * sizeof(real), S->st));
     if (!(p->lowStorage && !p->rk4)) { if ((rc = dmalloc(S, &S->R2, 5 * S->N))) { cudns_destroy(S); return rc; } }
     if ((rc = dmalloc(S, &S->d_xp, mx)) || (rc = dmalloc(S, &S->d_dxv, mx)) || (rc = dmalloc(S, &S->d_cVSx, (size_t)mx * (2 * v + 1))) ||
         (rc = dmalloc(S, &S->d_scal, SC_N)) || (rc = dmalloc(S, &S->d_spx, mx)) || (rc = dmalloc(S, &S->d_spz, mzl)) ||
@@ -287,9 +298,9 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         for (int it = v + 1; it < 2 * v + 1; it++)
             for (int i = 0; i < mx; i++)
                 tab[i + (size_t)it * mx] = (cVS[2 * v - it] * (xp[i] * xp[i]) * h_d2x + cVF[2 * v - it] * xpp[i] * (xp[i] * xp[i] * xp[i]) * h_dx);
-        CKC(cudaMemcpy(S->d_dxv, dxv.data(), mx * sizeof(double), cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(S->d_cVSx, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CKC(cudaMemcpy(S->d_xp, xp, mx * sizeof(double), cudaMemcpyHostToDevice));
+        CKC(upload(S->d_dxv, dxv.data(), mx));
+        CKC(upload(S->d_cVSx, tab.data(), tab.size()));
+        CKC(upload(S->d_xp, xp, mx));
     }
     kc.xp = S->d_xp; kc.cVSx = S->d_cVSx; kc.dxv = S->d_dxv;
     kc.spongeX = nullptr; kc.spongeZ = nullptr; kc.sref = nullptr;
@@ -298,23 +309,23 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
     CKC(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
-    if ((size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    if (!kF32 && (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
         const int CXb = 32 + 2 * GX;
         const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lty + 2 * s;
-        for (int b = 0; b < S->nstate; b++) {
+        for (int b = 0; !kF32 && b < S->nstate; b++) {
             if ((rc = make_map(&S->lmaps[b].qbox, L, S->state[b], 5, CXb, LYb)) || (rc = make_map(&S->lmaps[b].qint, L, S->state[b], 5, 32, lty)) ||
                 (rc = make_map(&S->lmaps[b].thbox, L, S->theta, 1, CXb, LYb)) || (rc = make_map(&S->lmaps[b].thint, L, S->theta, 1, 32, lty))) {
                 cudns_destroy(S); return rc;
             }
         }
-        if ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty)))) { cudns_destroy(S); return rc; }
+        if (!kF32 && ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty))))) { cudns_destroy(S); return rc; }
         const char *we = getenv("CUDNS_WIDE");
-        S->wide = lean_wide_ok(kc) && !(we && std::string(we) == "0") && (size_t)lean_smem_wide_bytes(s) <= prop.sharedMemPerBlockOptin;
-        if (S->fast) {
+        S->wide = !kF32 && lean_wide_ok(kc) && !(we && std::string(we) == "0") && (size_t)lean_smem_wide_bytes(s) <= prop.sharedMemPerBlockOptin;
+        if (S->fast && !kF32) {
             const int fty = S->fast_ty, FYb = fty + 2 * s;
             for (int b = 0; b < S->nstate; b++) {
-                double *q = S->state[b];
+                real *q = S->state[b];
                 if ((rc = make_map(&S->fmaps[b].q4box, L, q, 4, CXb, FYb)) || (rc = make_map(&S->fmaps[b].a3box, L, q + 5 * L.vol, 3, CXb, FYb)) ||
                     (rc = make_map(&S->fmaps[b].q4int, L, q, 4, 32, fty)) || (rc = make_map(&S->fmaps[b].a3int, L, q + 5 * L.vol, 3, 32, fty)) ||
                     (rc = make_map(&S->fmaps[b].eint, L, q + 4 * L.vol, 1, 32, fty))) {
@@ -328,7 +339,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             S->theta_tma = p->periodicX && !p->nonUniformX && !p->boundaryLayer && mx % 2 == 0 && !(te && std::string(te) == "0") &&
                            (size_t)theta_tma_smem_bytes(v) <= prop.sharedMemPerBlockOptin;
             for (int b = 0; S->theta_tma && b < S->nstate; b++) {
-                double *q = S->state[b];
+                real *q = S->state[b];
                 if ((rc = make_map(&S->tmaps[b].u, L, q + L.vol, 1, THETA_TX + 2 * GX, THETA_TY)) ||
                     (rc = make_map(&S->tmaps[b].v, L, q + 2 * L.vol, 1, THETA_TX, THETA_TY + 2 * v)) ||
                     (rc = make_map(&S->tmaps[b].w, L, q + 3 * L.vol, 1, THETA_TX, THETA_TY))) {
@@ -337,9 +348,9 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             }
         }
         if (S->duo) {
-            const int DXb = DUO_TX + 2 * GX, DYb = DUO_TY + 2 * s;
+            const int DXb = DUO_TX + 2 * GX, DYb = duo_box_rows(s);
             for (int b = 0; b < S->nstate; b++) {
-                double *q = S->state[b];
+                real *q = S->state[b];
                 if ((rc = make_map(&S->dmaps[b].q4box, L, q, 4, DXb, DYb)) || (rc = make_map(&S->dmaps[b].a3box, L, q + 5 * L.vol, 3, DXb, DYb)) ||
                     (rc = make_map(&S->dmaps[b].q4int, L, q, 4, DUO_TX, DUO_TY)) || (rc = make_map(&S->dmaps[b].a3int, L, q + 5 * L.vol, 3, DUO_TX, DUO_TY))) {
                     cudns_destroy(S); return rc;
@@ -399,7 +410,7 @@ int cudns_halo_buffers(cudns_handle S, void **send_lo, void **send_hi, void **re
     if (!S) return CUDNS_EINVAL;
     if (send_lo) *send_lo = S->send_lo; if (send_hi) *send_hi = S->send_hi;
     if (recv_lo) *recv_lo = S->recv_lo; if (recv_hi) *recv_hi = S->recv_hi;
-    if (bytes_each) *bytes_each = S->halo_doubles * sizeof(double);
+    if (bytes_each) *bytes_each = S->halo_doubles * sizeof(real);
     return CUDNS_OK;
 }
 int cudns_halo_local_info(cudns_handle S, cudns_peer_info *mine) {
@@ -413,14 +424,14 @@ int cudns_halo_local_info(cudns_handle S, cudns_peer_info *mine) {
     mine->device = S->P.device;
     mine->pid = (int)getpid();
     mine->local_ptr = (uint64_t)(uintptr_t)S->block;
-    mine->block_bytes = (uint64_t)(S->block_doubles + 32) * sizeof(double);
+    mine->block_bytes = (uint64_t)(S->block_doubles + 32) * sizeof(real);
     return CUDNS_OK;
 }
 
 // map one neighbour's block: same process -> its pointer (peer access enabled), other process -> CUDA IPC
-static int open_peer(cudns_solver *S, const cudns_peer_info *pi, double **ptr, void **ipc) {
+static int open_peer(cudns_solver *S, const cudns_peer_info *pi, real **ptr, void **ipc) {
     *ptr = nullptr; *ipc = nullptr;
-    if (pi->block_bytes != (uint64_t)(S->block_doubles + 32) * sizeof(double)) { set_error("neighbour block size differs (unequal slabs?)"); return CUDNS_EINVAL; }
+    if (pi->block_bytes != (uint64_t)(S->block_doubles + 32) * sizeof(real)) { set_error("neighbour block size differs (unequal slabs?)"); return CUDNS_EINVAL; }
     if (pi->pid == (int)getpid()) {
         if (pi->device != S->P.device) {
             int can = 0; CK(cudaDeviceCanAccessPeer(&can, S->P.device, pi->device));
@@ -429,14 +440,14 @@ static int open_peer(cudns_solver *S, const cudns_peer_info *pi, double **ptr, v
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
             cudaGetLastError();
         }
-        *ptr = (double *)(uintptr_t)pi->local_ptr;
+        *ptr = (real *)(uintptr_t)pi->local_ptr;
         return CUDNS_OK;
     }
     cudaIpcMemHandle_t h; std::memcpy(&h, pi->mem_handle, sizeof(h));
     void *p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); return CUDNS_ECUDA; }
-    *ptr = (double *)p; *ipc = p;
+    *ptr = (real *)p; *ipc = p;
     return CUDNS_OK;
 }
 
@@ -463,7 +474,7 @@ int cudns_get_counters(cudns_handle S, uint64_t *kernel_launches, uint64_t *rk_s
 }  // extern "C"
 
 // z ghosts of a padded 5-field buffer: periodic wrap on one device, exchange with the slab neighbours otherwise
-static int fill_z_ghosts(cudns_solver *S, double *q) {
+static int fill_z_ghosts(cudns_solver *S, real *q) {
     if (S->P.nranks == 1) {
         if (!S->P.boundaryLayer) { launch_zwrap(S->kc, q, 5, S->st); S->launches++; }
         return CUDNS_OK;
@@ -532,30 +543,46 @@ int cudns_get_state_device(cudns_handle S, double *d_r, double *d_u, double *d_v
 int cudns_set_state(cudns_handle S, const double *r, const double *u, const double *v, const double *w, const double *e) {
     if (!S || !r || !u || !v || !w || !e) { set_error("NULL argument"); return CUDNS_EINVAL; }
     CK(cudaSetDevice(S->P.device));
-    // stage through the register array R1 (5*N doubles), exactly the staging role of d_fr.. in the reference
+    // stage through the register array R1 (5*N doubles), exactly the staging role of d_fr.. in the reference (single precision: R1 is
+    // half that size, the double staging block is allocated for the call)
     const double *src[5] = {r, u, v, w, e};
-    for (int f = 0; f < 5; f++) CK(cudaMemcpyAsync(S->R1 + f * S->N, src[f], S->N * sizeof(double), cudaMemcpyHostToDevice, S->st));
-    return cudns_set_state_device(S, S->R1, S->R1 + S->N, S->R1 + 2 * S->N, S->R1 + 3 * S->N, S->R1 + 4 * S->N);
+    double *stage = nullptr;
+    if (sizeof(real) == sizeof(double)) stage = reinterpret_cast<double *>(S->R1);
+    else CK(cudaMalloc((void **)&stage, 5 * S->N * sizeof(double)));
+    for (int f = 0; f < 5; f++) {
+        cudaError_t e2 = cudaMemcpyAsync(stage + f * S->N, src[f], S->N * sizeof(double), cudaMemcpyHostToDevice, S->st);
+        if (e2 != cudaSuccess) { if ((void *)stage != (void *)S->R1) cudaFree(stage); set_error(std::string("cudns_set_state: ") + cudaGetErrorString(e2)); return CUDNS_ECUDA; }
+    }
+    int rc = cudns_set_state_device(S, stage, stage + S->N, stage + 2 * S->N, stage + 3 * S->N, stage + 4 * S->N);
+    if ((void *)stage != (void *)S->R1) cudaFree(stage);
+    return rc;
 }
 
 // copyField(1), cuda_utils.cu:334-355.  Between steps the register array holds no live data for the
 // low-storage scheme's first stage (alpha_0 = 0) nor for Kutta/RK4, so it doubles as the staging buffer.
 int cudns_get_state(cudns_handle S, double *r, double *u, double *v, double *w, double *e) {
     if (!S || !r || !u || !v || !w || !e) { set_error("NULL argument"); return CUDNS_EINVAL; }
-    int rc = cudns_get_state_device(S, S->R1, S->R1 + S->N, S->R1 + 2 * S->N, S->R1 + 3 * S->N, S->R1 + 4 * S->N);
-    if (rc) return rc;
+    CK(cudaSetDevice(S->P.device));
+    double *stage = nullptr;
+    if (sizeof(real) == sizeof(double)) stage = reinterpret_cast<double *>(S->R1);
+    else CK(cudaMalloc((void **)&stage, 5 * S->N * sizeof(double)));
+    int rc = cudns_get_state_device(S, stage, stage + S->N, stage + 2 * S->N, stage + 3 * S->N, stage + 4 * S->N);
     double *dst[5] = {r, u, v, w, e};
-    for (int f = 0; f < 5; f++) CK(cudaMemcpyAsync(dst[f], S->R1 + f * S->N, S->N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
-    CK(cudaStreamSynchronize(S->st));
+    cudaError_t e2 = cudaSuccess;
+    for (int f = 0; f < 5 && !rc && e2 == cudaSuccess; f++) e2 = cudaMemcpyAsync(dst[f], stage + f * S->N, S->N * sizeof(double), cudaMemcpyDeviceToHost, S->st);
+    if (!rc && e2 == cudaSuccess) e2 = cudaStreamSynchronize(S->st);
+    if ((void *)stage != (void *)S->R1) cudaFree(stage);
+    if (rc) return rc;
+    if (e2 != cudaSuccess) { set_error(std::string("cudns_get_state: ") + cudaGetErrorString(e2)); return CUDNS_ECUDA; }
     return CUDNS_OK;
 }
 
 int cudns_set_sponge(cudns_handle S, const double *sigma_x, const double *sigma_z, const double *ref5) {
     if (!S || !sigma_x || !sigma_z || !ref5) { set_error("NULL argument"); return CUDNS_EINVAL; }
     CK(cudaSetDevice(S->P.device));
-    CK(cudaMemcpy(S->d_spx, sigma_x, S->L.mx * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(S->d_spz, sigma_z, S->L.mz * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(S->d_sref, ref5, 5 * (size_t)S->L.mx * S->L.mz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(upload(S->d_spx, sigma_x, S->L.mx));
+    CK(upload(S->d_spz, sigma_z, S->L.mz));
+    CK(upload(S->d_sref, ref5, 5 * (size_t)S->L.mx * S->L.mz));
     S->kc.spongeX = S->d_spx; S->kc.spongeZ = S->d_spz; S->kc.sref = S->d_sref;
     S->have_sponge = true;
     return CUDNS_OK;
@@ -607,7 +634,7 @@ static void launch_stage_any(cudns_solver *S, const StagePtrs &p, const StageCoe
         LeanMaps m;
         m.qbox = sm[in].qbox; m.qint = sm[in].qint; m.thbox = sm[in].thbox; m.thint = sm[in].thint;
         m.qbint = sm[base].qint;
-        auto rmap_of = [&](const double *r) -> const CUtensorMap & { return (r == S->R2) ? rm[1] : rm[0]; };
+        auto rmap_of = [&](const real *r) -> const CUtensorMap & { return (r == S->R2) ? rm[1] : rm[0]; };
         m.opa = rmap_of(p.RA);
         m.opb = rmap_of(p.RB ? p.RB : p.RW);
         launch_rhs_stage_lean(S->kc, p, c, m, wide, S->st);
@@ -650,8 +677,8 @@ static void handshake(cudns_solver *S) {
 }
 
 // one RHS evaluation + register update: K = RHS(state[in]); see StageCoef
-static int run_stage(cudns_solver *S, int in, int base, int out, const double *RA, const double *RB, double *RW,
-                     const StageCoef &c, double *rhs_out) {
+static int run_stage(cudns_solver *S, int in, int base, int out, const real *RA, const real *RB, real *RW,
+                     const StageCoef &c, real *rhs_out) {
     StagePtrs p;
     p.qin = S->state[in]; p.qbase = S->state[base]; p.qout = S->state[out]; p.theta = S->theta;
     p.RA = RA; p.RB = RB; p.RW = RW; p.rhs_out = rhs_out;
@@ -660,8 +687,8 @@ static int run_stage(cudns_solver *S, int in, int base, int out, const double *R
     StageTimer *tm = (S->tm && S->tm->on && !rhs_out && S->tm->used + 4 <= S->tm->ev.size()) ? S->tm : nullptr;
     cudaEvent_t *tev = tm ? &tm->ev[tm->used] : nullptr;
     if (tm) { tm->used += 4; cudaEventRecord(tev[0], S->st); }
-    if (S->theta_tma) launch_theta_tma(S->kc, S->state[in], const_cast<double *>(p.theta), S->tmaps[in], S->st);
-    else launch_theta(S->kc, S->state[in], const_cast<double *>(p.theta), S->st);
+    if (S->theta_tma) launch_theta_tma(S->kc, S->state[in], const_cast<real *>(p.theta), S->tmaps[in], S->st);
+    else launch_theta(S->kc, S->state[in], const_cast<real *>(p.theta), S->st);
     if (tm) cudaEventRecord(tev[1], S->st);
     ghost_targets(S, out, p);
     if (rhs_out) { p.qout_lo = nullptr; p.qout_hi = nullptr; }
@@ -709,14 +736,20 @@ int cudns_calc_rhs(cudns_handle S, double *rhs_r, double *rhs_u, double *rhs_v, 
     if (!S) { set_error("NULL handle"); return CUDNS_EINVAL; }
     if (!S->have_state) { set_error("no state set"); return CUDNS_ESTATE; }
     CK(cudaSetDevice(S->P.device));
-    double *tmp = nullptr;
-    CK(cudaMalloc((void **)&tmp, 5 * S->N * sizeof(double)));
+    real *tmp = nullptr;
+    CK(cudaMalloc((void **)&tmp, 5 * S->N * sizeof(real)));
     StageCoef c = {1, 0, 0, 0, 0};
     int rc = run_stage(S, S->cur, S->cur, S->cur, nullptr, nullptr, nullptr, c, tmp);
     if (rc) { cudaFree(tmp); return rc; }
     double *dst[5] = {rhs_r, rhs_u, rhs_v, rhs_w, rhs_e};
-    for (int f = 0; f < 5; f++)
-        if (dst[f]) CK(cudaMemcpyAsync(dst[f], tmp + f * S->N, S->N * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    std::vector<real> hbuf(sizeof(real) == sizeof(double) ? 0 : S->N);          // single precision: widened on the host
+    for (int f = 0; f < 5; f++) {
+        if (!dst[f]) continue;
+        if (sizeof(real) == sizeof(double)) { CK(cudaMemcpyAsync(dst[f], tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st)); continue; }
+        CK(cudaMemcpyAsync(hbuf.data(), tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st));
+        CK(cudaStreamSynchronize(S->st));
+        for (size_t n = 0; n < S->N; n++) dst[f][n] = (double)hbuf[n];
+    }
     CK(cudaStreamSynchronize(S->st));
     cudaFree(tmp);
     return CUDNS_OK;
@@ -921,8 +954,8 @@ int cudns_profile_stage(cudns_handle S, int reps, float *ms_theta, float *ms_rhs
             p.theta = S->state[a] + 7 * S->L.vol;
             if (!S->aux_valid[a]) { launch_derive_aux(S->kc, S->state[a], S->st); S->aux_valid[a] = true; }
         }
-        if (S->theta_tma) launch_theta_tma(S->kc, S->state[a], const_cast<double *>(p.theta), S->tmaps[a], S->st);
-        else launch_theta(S->kc, S->state[a], const_cast<double *>(p.theta), S->st);
+        if (S->theta_tma) launch_theta_tma(S->kc, S->state[a], const_cast<real *>(p.theta), S->tmaps[a], S->st);
+        else launch_theta(S->kc, S->state[a], const_cast<real *>(p.theta), S->st);
         CK(cudaEventRecord(e1, S->st));
         ghost_targets(S, b, p);
         launch_stage_any(S, p, c, a, ls ? a : (a + 2) % 3);
@@ -1104,7 +1137,7 @@ int cudns_calc_profiles(cudns_handle S, double *prof) {
     const int mx = S->L.mx;
     double *partial = S->d_prof, *mean = partial + profile_partial_doubles(S->kc), *var = mean + 5 * mx;
     const double scale = 1.0 / ((double)S->P.my * (double)S->P.mz);        // global row count: slabs add up to the whole plane
-    const double *q = S->state[S->cur];
+    const real *q = S->state[S->cur];
     launch_profile_partial(S->kc, q, nullptr, partial, 0, S->st);
     launch_profile_combine(S->kc, partial, mean, scale, S->st);
     reduce_across(S, mean, 5 * mx, 1);

@@ -7,9 +7,42 @@
 #include <mutex>
 #include <string>
 #include <vector>
+
+// Host-side helpers shared by both precisions (defined once, host_setup.cpp)
+struct cudns_params;
+namespace cudns_shared {
+void set_error(const std::string &msg);
+const double *coeff_first(int s);
+const double *coeff_second(int s);
+int check_params(const cudns_params *p);
+}  // namespace cudns_shared
+
+// ---- precision (`myprec` of the reference, src/globals.h:5-6).  The device side -- kernels, coefficient tables, the solver object --
+// is compiled twice: as is (real = double) and with -DCUDNS_F32 (real = float; the translation units that carry it are listed in the
+// Makefile).  The single-precision copy lives in namespace cudns32 and exports its C entry points as cudns32_* (cudns_abi.h); the
+// public symbols of include/cudns.h dispatch on the precision recorded in the handle (abi_dispatch.cpp).  Host arrays that cross
+// the C ABI are double in both builds, like the reference's (copyField casts, cuda_utils.cu:317-355).
+#ifdef CUDNS_F32
+#define cudns cudns32
+#endif
+#include "cudns_abi.h"
 #include "../../include/cudns.h"
 
 namespace cudns {
+using namespace cudns_shared;
+#ifdef CUDNS_F32
+typedef float real;
+typedef float2 real2;
+typedef float4 vec16;                                   // 16 bytes of state
+#define CUDNS_TMA_REAL CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+#else
+typedef double real;
+typedef double2 real2;
+typedef double2 vec16;
+#define CUDNS_TMA_REAL CU_TENSOR_MAP_DATA_TYPE_FLOAT64
+#endif
+constexpr int VEC16 = 16 / (int)sizeof(real);           // state elements per 16 bytes
+#define RC(x) ((real)(x))                               // literal of the working precision
 
 constexpr int GX = 4;            // x ghost width in memory (>= s, even: keeps interior rows 16B aligned)
 constexpr int MAXS = 4;
@@ -31,29 +64,30 @@ struct KConst {
     int s, v;
     int kstart;                  // global index of local plane 0 (perturbation strip, sponge)
     int mz_tot;
-    double d1[3], d2[3];         // 1/Delta, 1/Delta^2 per direction (d_dx.. d_d2z, cuda_utils.cu:61-63,88-90)
-    double aF[MAXS + 1];         // advective first-derivative weights a_l, l=1..s ( = -coeffF[s-l], globals.h:69-82)
-    double aV[MAXS + 1];         // viscous   first-derivative weights
-    double bV[MAXS + 1];         // viscous second-derivative weights b_0..b_v ( = coeffVS[v-l] )
+    real d1[3], d2[3];         // 1/Delta, 1/Delta^2 per direction (d_dx.. d_d2z, cuda_utils.cu:61-63,88-90)
+    real aF[MAXS + 1];         // advective first-derivative weights a_l, l=1..s ( = -coeffF[s-l], globals.h:69-82)
+    real aV[MAXS + 1];         // viscous   first-derivative weights
+    real bV[MAXS + 1];         // viscous second-derivative weights b_0..b_v ( = coeffVS[v-l] )
     // the same weights pre-scaled by the grid spacing of direction d: c1 = a_l/dx_d (viscous order; dilatation pass)
-    double c1[3][MAXS + 1];
+    real c1[3][MAXS + 1];
     // stage kernels: cf[d][l] = { -a_l/(4 dx_d), -a_l/dx_d (advective order), a_l/dx_d, b_l/dx_d^2 (viscous order) },
     // c1t = a_l/(3 dx_d) (viscous order), c20sum = sum_d b_0/dx_d^2
-    double cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
-    double cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
-    double cfp[3][MAXS + 1];     // -a_l Rgas / dx_d: pressure gradient from rho*T in every direction (fast variant)
-    double gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
+    real cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
+    real cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
+    real cfp[3][MAXS + 1];     // -a_l Rgas / dx_d: pressure gradient from rho*T in every direction (fast variant)
+    real gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
-    double TwallTop, TwallBot;
+    real TwallTop, TwallBot;
     // perturbation.h
-    int kC, LP; double amp1, amp2, omega1, omega2, lambdaP;
-    double Lx, Ly, Lz, CFL;
-    const double *xp;            // [mx]  1/x'(xi)           (device)
-    const double *cVSx;          // [(2v+1)*mx] non-uniform second-derivative table (device)
-    const double *dxv;           // [mx] cell widths          (device)
-    const double *spongeX, *spongeZ, *sref;   // [mx], [mz], [5][mx*mz]
-    const double *dt, *dpdz, *time_on_gpu;    // device scalars
+    int kC, LP; real amp1, amp2, omega1, omega2, lambdaP;
+    real Lx, Ly, Lz, CFL;
+    const real *xp;            // [mx]  1/x'(xi)           (device)
+    const real *cVSx;          // [(2v+1)*mx] non-uniform second-derivative table (device)
+    const real *dxv;           // [mx] cell widths          (device)
+    const real *spongeX, *spongeZ, *sref;   // [mx], [mz], [5][mx*mz]
+    const double *dt, *dpdz, *time_on_gpu;  // device scalars: double in both builds, like every reduced scalar and statistic (the
+                                            // cross-rank all-reduce callback moves doubles)
 };
 
 // One Runge-Kutta stage as a generic register update (see DESIGN.md "RK algebra"):
@@ -61,20 +95,20 @@ struct KConst {
 //   Q_out  = Q_base + dt*( cN*K + cA*RA + cB*RB )        (conservative; stored primitive)
 //   RW     = wOld*RW + wNew*K                             (skipped when RW == nullptr)
 struct StageCoef {
-    double cN, cA, cB, wOld, wNew;
+    real cN, cA, cB, wOld, wNew;
 };
 
 struct StagePtrs {
-    const double *qin;           // 5 padded fields, stride L.vol
-    const double *qbase;         // 5 padded fields (may equal qin)
-    double *qout;                // 5 padded fields
-    const double *theta;         // padded
-    const double *RA, *RB;       // 5 unpadded fields each (stride N) or nullptr
-    double *RW;                  // 5 unpadded fields or nullptr
-    double *qout_lo, *qout_hi;   // lean kernel: the SAME output buffer on the lower / upper z neighbour (peer memory over NVLink,
+    const real *qin;           // 5 padded fields, stride L.vol
+    const real *qbase;         // 5 padded fields (may equal qin)
+    real *qout;                // 5 padded fields
+    const real *theta;         // padded
+    const real *RA, *RB;       // 5 unpadded fields each (stride N) or nullptr
+    real *RW;                  // 5 unpadded fields or nullptr
+    real *qout_lo, *qout_hi;   // lean kernel: the SAME output buffer on the lower / upper z neighbour (peer memory over NVLink,
                                  // or qout itself for the periodic wrap on one device); the stage kernel stores its first / last
                                  // gz planes straight into the neighbour's ghost planes.  nullptr: no such neighbour / not connected
-    double *rhs_out;             // test path: write K only (5 unpadded) and skip the update
+    real *rhs_out;             // test path: write K only (5 unpadded) and skip the update
 };
 
 // TMA descriptors of one state buffer (+ theta) for the stage kernel: the tile with its x/y stencil halos
@@ -108,49 +142,52 @@ struct FastMaps {
 void launch_rhs_stage_fast(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, int ty, cudaStream_t st);
 // fifth-generation kernel (stage_duo.inc): tile 64 x 8, two x-adjacent points per thread; same 8-field state buffers; needs an even mx
 constexpr int DUO_TX = 64, DUO_TY = 8;
+// rows of its halo'd plane: 8 + 2s, rounded up until one field of the box is a multiple of 128 bytes (TMA destinations; single
+// precision with s = 1, 3 only)
+constexpr int duo_box_rows(int s) { int cy = DUO_TY + 2 * s; while (((DUO_TX + 2 * GX) * cy * (int)sizeof(real)) % 128) cy++; return cy; }
 struct DuoMaps {
     CUtensorMap q4box, a3box;               // halo'd tile (72 x (8+2s)) of (rho,u,v,w) and of (H,T,theta)
     CUtensorMap q4int, a3int;               // tile interior (64 x 8) of the same (plane S ahead, for the z ring)
 };
 void launch_rhs_stage_duo(const KConst &kc, const StagePtrs &p, const StageCoef &c, const DuoMaps &maps, cudaStream_t st);
 int duo_smem_bytes(int s);
-void launch_derive_aux(const KConst &kc, double *q8, cudaStream_t st);
+void launch_derive_aux(const KConst &kc, real *q8, cudaStream_t st);
 int fast_smem_bytes(int s, int ty);
 int lean_smem_wide_bytes(int s);
 #define CUDNS_LEAN_TY_WIDE 16
 int lean_smem_bytes(int s, bool linear_visc);
 
-void launch_theta(const KConst &kc, const double *q, double *theta, cudaStream_t st);
+void launch_theta(const KConst &kc, const real *q, real *theta, cudaStream_t st);
 // TMA variant of the dilatation pass (theta.cu) for the periodic / uniform set-ups with an even mx: boxes of u (72 x 16, x halos),
 // v (64 x (16 + 2v), y halos) and w (64 x 16) of one padded state buffer
 constexpr int THETA_TX = 64, THETA_TY = 16;
 struct ThetaMaps { CUtensorMap u, v, w; };
-void launch_theta_tma(const KConst &kc, const double *q, double *theta, const ThetaMaps &maps, cudaStream_t st);
+void launch_theta_tma(const KConst &kc, const real *q, real *theta, const ThetaMaps &maps, cudaStream_t st);
 int theta_tma_smem_bytes(int v);
-void launch_fill_xy(const KConst &kc, double *q5, int nfields, cudaStream_t st);
-void launch_zwrap(const KConst &kc, double *q5, int nfields, cudaStream_t st);
-void launch_pack_z(const KConst &kc, const double *q5, double *send_lo, double *send_hi, cudaStream_t st);
-void launch_unpack_z(const KConst &kc, double *q5, const double *recv_lo, const double *recv_hi, cudaStream_t st);
-void launch_pad(const KConst &kc, const double *src5[5], double *q5, cudaStream_t st);
-void launch_unpad(const KConst &kc, const double *q5, double *dst5[5], cudaStream_t st);
+void launch_fill_xy(const KConst &kc, real *q5, int nfields, cudaStream_t st);
+void launch_zwrap(const KConst &kc, real *q5, int nfields, cudaStream_t st);
+void launch_pack_z(const KConst &kc, const real *q5, real *send_lo, real *send_hi, cudaStream_t st);
+void launch_unpack_z(const KConst &kc, real *q5, const real *recv_lo, const real *recv_hi, cudaStream_t st);
+void launch_pad(const KConst &kc, const double *src5[5], real *q5, cudaStream_t st);      // the caller's arrays are double in both builds
+void launch_unpad(const KConst &kc, const real *q5, double *dst5[5], cudaStream_t st);
 // reductions: out[0] = max_p conv limiter, out[1] = max_p visc limiter (uses fresh mu), out[2..] sums
-void launch_dt_reduce(const KConst &kc, const double *q, double *out2, cudaStream_t st);
+void launch_dt_reduce(const KConst &kc, const real *q, double *out2, cudaStream_t st);
 // scratch: bulk_scratch_doubles() doubles owned by the calling solver (block partials, then the completion counter; zeroed once)
-void launch_bulk_reduce(const KConst &kc, const double *q, double *out4, double *scratch, cudaStream_t st);
+void launch_bulk_reduce(const KConst &kc, const real *q, double *out4, double *scratch, cudaStream_t st);
 int bulk_scratch_doubles();
 // mean square vorticity of a periodic box (same scratch)
-void launch_enstrophy_reduce(const KConst &kc, const double *q, double *out, double *scratch, cudaStream_t st);
+void launch_enstrophy_reduce(const KConst &kc, const real *q, double *out, double *scratch, cudaStream_t st);
 void launch_scalar_ops(int op, double *a, const double *b, const double *c, cudaStream_t st);
 // wall-normal profiles / friction Reynolds number (calcAvgChan, printRes): see kernels.cu
-void launch_profile_partial(const KConst &kc, const double *q, const double *mean, double *partial, int pass, cudaStream_t st);
+void launch_profile_partial(const KConst &kc, const real *q, const double *mean, double *partial, int pass, cudaStream_t st);
 void launch_profile_combine(const KConst &kc, const double *partial, double *out, double scale, cudaStream_t st);
 void launch_profile_favre(const KConst &kc, double *mean, cudaStream_t st);
 int profile_partial_doubles(const KConst &kc);
-void launch_retau(const KConst &kc, const double *q, double *partial, double *out, double scale, cudaStream_t st);
+void launch_retau(const KConst &kc, const real *q, double *partial, double *out, double scale, cudaStream_t st);
 // post-processing statistics (postproc/post.cpp): see kernels.cu.  acc[13][mx] += scale * (sums | squared deviations from mean)
 int post_partial_doubles(const KConst &kc);
-void launch_post_accumulate(const KConst &kc, const double *q, const double *mean, double *partial, double *acc, double scale, int pass, cudaStream_t st);
-void launch_post_ret(const KConst &kc, const double *q, double host_dx, double *partial, double *ret2, double scale, cudaStream_t st);
+void launch_post_accumulate(const KConst &kc, const real *q, const double *mean, double *partial, double *acc, double scale, int pass, cudaStream_t st);
+void launch_post_ret(const KConst &kc, const real *q, double host_dx, double *partial, double *ret2, double scale, cudaStream_t st);
 void launch_post_finish_mean(const KConst &kc, double *mean, double *bulk, double *ret2, double inv_files, cudaStream_t st);
 // cross-GPU stage hand-shake over peer memory: store `epoch` into the two neighbours' mailbox slots / spin until both own slots reach it
 void launch_halo_signal(unsigned long long *peer_lo_slot, unsigned long long *peer_hi_slot, unsigned long long epoch, cudaStream_t st);
@@ -174,6 +211,5 @@ inline void opt_in_smem(int bytes) {
 
 bool rhs_stage_supported(int s, int v);
 
-void set_error(const std::string &msg);
 
 }  // namespace cudns

@@ -34,7 +34,7 @@ const Field kFields[] = {
     F_I(boundaryLayer), F_I(perturbed), F_I(forcing), F_I(periodicX), F_I(nonUniformX), F_I(checkCFLcondition), F_I(checkBulk),
     F_D(Re), F_D(Pr), F_D(Ma), F_D(viscexp), F_D(gam), F_D(stretch), F_D(TwallTop), F_D(TwallBot),
     F_D(spTopStr), F_D(spTopLen), F_D(spTopExp), F_D(spInlStr), F_D(spInlLen), F_D(spInlExp), F_D(spOutStr), F_D(spOutLen), F_D(spOutExp),
-    F_I(kC), F_I(LP), F_D(amp1), F_D(amp2), F_D(omega1), F_D(omega2), F_I(quirk_q1), F_I(rk4), F_I(device), F_I(par2_enstrophy)};
+    F_I(kC), F_I(LP), F_D(amp1), F_D(amp2), F_D(omega1), F_D(omega2), F_I(quirk_q1), F_I(rk4), F_I(device), F_I(par2_enstrophy), F_I(precision)};
 
 void die(const std::string &msg) { std::fprintf(stderr, "cudns_run: %s\n", msg.c_str()); std::exit(1); }
 #define CK(call) do { if ((call) != CUDNS_OK) die(std::string(#call) + ": " + cudns_last_error()); } while (0)

@@ -9,7 +9,7 @@
 #include <cstring>
 #include <vector>
 
-namespace cudns {
+namespace cudns_shared {
 static thread_local std::string g_err;
 void set_error(const std::string &m) { g_err = m; }
 
@@ -38,12 +38,13 @@ int check_params(const cudns_params *p) {
     if (p->mx % 2) { set_error("mx must be even (16-byte row alignment; the reference needs mx % sPencils == 0)"); return CUDNS_EINVAL; }
     if (!(p->Re > 0) || !(p->Ma > 0) || !(p->Pr > 0) || !(p->gam > 1)) { set_error("Re, Ma, Pr must be > 0 and gam > 1"); return CUDNS_EINVAL; }
     if (p->checkCFLcondition < 1 || p->checkBulk < 1) { set_error("checkCFLcondition / checkBulk must be >= 1"); return CUDNS_EINVAL; }
+    if (p->precision != 0 && p->precision != 1) { set_error("precision must be 0 (double) or 1 (float)"); return CUDNS_EINVAL; }
     if (p->boundaryLayer && p->periodicX) { set_error("boundaryLayer requires periodicX = 0"); return CUDNS_EINVAL; }
     return CUDNS_OK;
 }
-}  // namespace cudns
+}  // namespace cudns_shared
 
-using namespace cudns;
+using namespace cudns_shared;
 
 extern "C" {
 

@@ -1,5 +1,6 @@
 // dispatcher of the fifth-generation stage kernel over the stencil half-width (instantiations: stage_duo_s1..4.cu)
 #include "cudns_internal.h"
+#include "stage_point.h"
 namespace cudns {
 void launch_duo_s1(const KConst &, const StagePtrs &, const StageCoef &, const DuoMaps &, cudaStream_t);
 void launch_duo_s2(const KConst &, const StagePtrs &, const StageCoef &, const DuoMaps &, cudaStream_t);
@@ -20,4 +21,28 @@ void launch_rhs_stage_duo(const KConst &kc, const StagePtrs &p, const StageCoef 
 int duo_smem_bytes(int s) {
     switch (s) { case 1: return duo_smem_s1(); case 2: return duo_smem_s2(); case 3: return duo_smem_s3(); default: return duo_smem_s4(); }
 }
+
+// H, T of every cell of a padded 8-field state buffer (ghosts included) from its (rho,u,v,w,rho*E): for buffers the stage kernel did
+// not write itself (cudns_set_state, the lean kernels, a separate ghost exchange)
+__global__ void __launch_bounds__(256) derive_aux_kernel(const __grid_constant__ KConst c, real *__restrict__ q8) {
+    const size_t vol = c.L.vol;
+    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < vol; n += (size_t)gridDim.x * blockDim.x) {
+        const real r = q8[n], u = q8[vol + n], v = q8[2 * vol + n], w = q8[3 * vol + n], e = q8[4 * vol + n];
+        real H, T;
+        fast::eos_ht(c, r, RC(1.0) / r, u, v, w, e, H, T);
+        q8[5 * vol + n] = H; q8[6 * vol + n] = T;
+    }
+}
+void launch_derive_aux(const KConst &kc, real *q8, cudaStream_t st) { derive_aux_kernel<<<148 * 8, 256, 0, st>>>(kc, q8); }
+
+#ifdef CUDNS_F32
+// the older kernel generations exist in double precision only (api.cu never selects them in this build)
+void launch_rhs_stage_lean(const KConst &, const StagePtrs &, const StageCoef &, const LeanMaps &, bool, cudaStream_t) {}
+void launch_rhs_stage_fast(const KConst &, const StagePtrs &, const StageCoef &, const FastMaps &, int, cudaStream_t) {}
+bool lean_wide_ok(const KConst &) { return false; }
+int lean_smem_wide_bytes(int) { return 0; }
+int lean_smem_bytes(int, bool) { return 0; }
+int fast_smem_bytes(int, int) { return 0; }
+void launch_theta_march(const KConst &, const real *, real *, cudaStream_t);
+#endif
 }  // namespace cudns

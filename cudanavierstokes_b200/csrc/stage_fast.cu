@@ -427,17 +427,6 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     if ((tid_now() >> 5) == 0) tmem_dealloc(lds_u32_now(smem_u32(tmem_holder)), G::NCOLS);
 }
 
-// H, T of every cell of a padded 8-field state buffer (ghosts included) from its (rho,u,v,w,rho*E): for buffers this kernel did not write
-__global__ void __launch_bounds__(256) derive_aux_kernel(const __grid_constant__ KConst c, double *__restrict__ q8) {
-    const size_t vol = c.L.vol;
-    for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < vol; n += (size_t)gridDim.x * blockDim.x) {
-        const double r = q8[n], u = q8[vol + n], v = q8[2 * vol + n], w = q8[3 * vol + n], e = q8[4 * vol + n];
-        double H, T;
-        eos_ht(c, r, 1.0 / r, u, v, w, e, H, T);
-        q8[5 * vol + n] = H; q8[6 * vol + n] = T;
-    }
-}
-
 template <int S, int V, int TY>
 static void launch_t(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, cudaStream_t st) {
     using G = FCfg<S, TY>;
@@ -478,9 +467,6 @@ static void launch_ty(const KConst &kc, const StagePtrs &p, const StageCoef &c, 
 // ty = 16: one CTA of 16 warps per SM, ty = 8: two CTAs of 8 warps (the TMA descriptors must have been built for that tile)
 void launch_rhs_stage_fast(const KConst &kc, const StagePtrs &p, const StageCoef &c, const FastMaps &maps, int ty, cudaStream_t st) {
     if (ty == 16) fast::launch_ty<16>(kc, p, c, maps, st); else fast::launch_ty<8>(kc, p, c, maps, st);
-}
-void launch_derive_aux(const KConst &kc, double *q8, cudaStream_t st) {
-    fast::derive_aux_kernel<<<148 * 8, 256, 0, st>>>(kc, q8);
 }
 int fast_smem_bytes(int s, int ty) {
     using namespace fast;

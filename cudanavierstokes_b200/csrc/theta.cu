@@ -24,23 +24,23 @@ constexpr int TXT = 32, TYT = 16, NTT = TXT * TYT;
 constexpr int UX = TXT + 2 * GX;
 constexpr int NST = 4;                                   // cp.async ring depth (planes)
 
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ void cp_async8(real *smem_dst, const real *gsrc) {        // one element
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "n"(sizeof(real)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // wall blowing/suction, perturbation.h:25-53
-__device__ __forceinline__ bool perturb_theta(const KConst &c, int j, int kglob, double &val) {
+__device__ __forceinline__ bool perturb_theta(const KConst &c, int j, int kglob, real &val) {
     int kSt = c.kC - c.LP / 2, kEn = c.kC + c.LP / 2;
     if (kglob < kSt || kglob > kEn) return false;
     int alpha, beta, kappa;
     if (kglob < c.kC) { kappa = 1; alpha = kglob - kSt; beta = c.kC - kSt; }
     else              { kappa = -1; alpha = kEn - kglob; beta = kEn - c.kC; }
-    double ksi = alpha * 1.0 / beta;
-    double g = (15.1875 * ksi * ksi * ksi * ksi * ksi) - (35.4375 * ksi * ksi * ksi * ksi) + (20.25 * ksi * ksi * ksi);
-    double y_glob = (double)j / c.d1[1];
-    double tg = *c.time_on_gpu;
+    real ksi = alpha * 1.0 / beta;
+    real g = (15.1875 * ksi * ksi * ksi * ksi * ksi) - (35.4375 * ksi * ksi * ksi * ksi) + (20.25 * ksi * ksi * ksi);
+    real y_glob = (real)j / c.d1[1];
+    real tg = *c.time_on_gpu;
     val = c.amp1 * kappa * g * sin(c.omega1 * tg) + c.amp2 * kappa * g * sin(c.omega2 * tg) * cos(y_glob / c.lambdaP);
     return true;
 }
@@ -49,13 +49,13 @@ __device__ __forceinline__ bool perturb_theta(const KConst &c, int j, int kglob,
 // botBCzExt / topBCzExt (boundary.h:154-160): dw/dz next to the global z boundaries of the boundary-layer case, where w
 // past the boundary is the node extrapolation f[-g] = 2 f[0] - f[g], f[mz-1+g] = 2 f[mz-1] - f[mz-1-g] (slow path)
 template <int V>
-__device__ __forceinline__ double dwdz_edge(const KConst &c, const double *__restrict__ W, int ic, int jc, int k, int kglob_lo, int kglob_hi) {
+__device__ __forceinline__ real dwdz_edge(const KConst &c, const real *__restrict__ W, int ic, int jc, int k, int kglob_lo, int kglob_hi) {
     const Layout &L = c.L;
     const size_t g0 = L.idx(ic, jc, k);
-    double dwdz = 0.0;
+    real dwdz = 0.0;
 #pragma unroll
     for (int l = 1; l <= V; l++) {
-        double wp, wm;
+        real wp, wm;
         if (k + l >= kglob_hi) wp = 2.0 * W[L.idx(ic, jc, kglob_hi - 1)] - W[L.idx(ic, jc, 2 * (kglob_hi - 1) - (k + l))];
         else wp = W[g0 + (size_t)l * L.plane];
         if (k - l < kglob_lo) wm = 2.0 * W[L.idx(ic, jc, kglob_lo)] - W[L.idx(ic, jc, 2 * kglob_lo - (k - l))];
@@ -67,13 +67,13 @@ __device__ __forceinline__ double dwdz_edge(const KConst &c, const double *__res
 
 template <int V, bool GEN>
 __global__ void __launch_bounds__(NTT, 2)
-theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ q, double *__restrict__ theta, int zchunk) {
+theta_march_kernel(const __grid_constant__ KConst c, const real *__restrict__ q, real *__restrict__ theta, int zchunk) {
     constexpr int VY = TYT + 2 * V;
     constexpr int SU = TYT * UX, SV = VY * TXT, SW = NTT;  // doubles per stage
-    extern __shared__ __align__(16) double sth[];
-    double *su = sth;                                     // [NST][TYT][UX]
-    double *sv = su + NST * SU;                           // [NST][VY][TXT]
-    double *sw = sv + NST * SV;                           // [NST][TYT][TXT]
+    extern __shared__ __align__(16) real sth[];
+    real *su = sth;                                     // [NST][TYT][UX]
+    real *sv = su + NST * SU;                           // [NST][VY][TXT]
+    real *sw = sv + NST * SV;                           // [NST][TYT][TXT]
 
     const Layout &L = c.L;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -98,17 +98,17 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
     const bool hx_load = hx_on && (perx || (hgi >= 0 && hgi < L.mx));
     const bool hy_on = ty < 2 * V && inx;
     const int hyr = ty < V ? ty : V + nyt + (ty - V);                     // row in sv
-    const double *pu = q + L.vol + g00, *pv = q + 2 * L.vol + g00, *pw = q + 3 * L.vol + g00 + (size_t)V * plane;
-    const double *puh = q + L.vol + L.idx(min(max(hgi, -GX), L.mx + GX - 1), jc, kfirst);
-    const double *pvh = q + 2 * L.vol + L.idx(ic, j0 + hyr - V, kfirst);
-    double *pt = theta + g00;
-    const double xpi = (GEN && c.nonUniformX) ? c.xp[ic] : 1.0;
+    const real *pu = q + L.vol + g00, *pv = q + 2 * L.vol + g00, *pw = q + 3 * L.vol + g00 + (size_t)V * plane;
+    const real *puh = q + L.vol + L.idx(min(max(hgi, -GX), L.mx + GX - 1), jc, kfirst);
+    const real *pvh = q + 2 * L.vol + L.idx(ic, j0 + hyr - V, kfirst);
+    real *pt = theta + g00;
+    const real xpi = (GEN && c.nonUniformX) ? c.xp[ic] : 1.0;
     // shared-memory slots (doubles, buffer 0)
     const int o_u = ty * UX + GX + tx, o_uh = ty * UX + hxc, o_v = (V + ty) * TXT + tx, o_vh = hyr * TXT + tx;
     // image flags: 1 x-low, 2 x-high, 4 y-low, 8 y-high (perBCx / perBCy, boundary.h:38-46)
     const unsigned img = ((perx && i < V) ? 1u : 0u) | ((perx && i >= L.mx - V) ? 2u : 0u) | ((j < V) ? 4u : 0u) | ((j >= L.my - V) ? 8u : 0u);
 
-    double wr[2 * V + 1];                                 // wr[V + l] = w of plane k+l
+    real wr[2 * V + 1];                                 // wr[V + l] = w of plane k+l
 #pragma unroll
     for (int m = 0; m < 2 * V; m++) wr[m + 1] = pw[(ptrdiff_t)(m - 2 * V) * (ptrdiff_t)plane];
     // plane kk (u, v at kk; w at kk+V) -> ring stage st; every thread commits exactly one group per call
@@ -141,12 +141,12 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
             if (xlo || xhi) {
                 // BCxderVel: wall (anti-mirror about the face, + blowing/suction) / node extrapolation at the free stream
                 if (hx_on && !hx_load && !outside) {
-                    const double *row = su + boff_u + ty * UX;
-                    double val;
+                    const real *row = su + boff_u + ty * UX;
+                    real val;
                     if (tx < V) {
                         const int gq = V - tx;                            // ghost -gq
                         val = -row[GX + gq - 1];
-                        double pv2;
+                        real pv2;
                         if (bl && c.perturbed && perturb_theta(c, j, k + c.kstart, pv2)) val = pv2;
                     } else {
                         const int gq = tx - V + 1, last = GX + nxt - 1;
@@ -158,9 +158,9 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
             }
         }
         if (active && !outside) {
-            double dudx = 0.0, dvdy = 0.0, dwdz = 0.0;
-            const double *ur = su + boff_u + o_u;
-            const double *vr = sv + boff_v + o_v;
+            real dudx = 0.0, dvdy = 0.0, dwdz = 0.0;
+            const real *ur = su + boff_u + o_u;
+            const real *vr = sv + boff_v + o_v;
 #pragma unroll
             for (int l = 1; l <= V; l++) {
                 dudx = fma(c.c1[0][l], ur[l] - ur[-l], dudx);
@@ -172,7 +172,7 @@ theta_march_kernel(const __grid_constant__ KConst c, const double *__restrict__ 
 #pragma unroll
                 for (int l = 1; l <= V; l++) dwdz = fma(c.c1[2][l], wr[V + l] - wr[V - l], dwdz);
             }
-            const double th = (GEN ? fma(dudx, xpi, dvdy) : dudx + dvdy) + dwdz;
+            const real th = (GEN ? fma(dudx, xpi, dvdy) : dudx + dvdy) + dwdz;
             *pt = th;
             if (img) {
                 if (img & 1u) pt[L.mx] = th;
@@ -206,22 +206,28 @@ __device__ __forceinline__ void th_tma_3d(uint32_t dst, const CUtensorMap *map, 
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"((uint64_t)map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void th_stg2(double *p, double a, double b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory"); }
+#ifdef CUDNS_F32
+__device__ __forceinline__ void th_stg2(real *p, real a, real b) { asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory"); }
+__device__ __forceinline__ real2 make_real2(real a, real b) { return make_float2(a, b); }
+#else
+__device__ __forceinline__ void th_stg2(real *p, real a, real b) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory"); }
+__device__ __forceinline__ real2 make_real2(real a, real b) { return make_double2(a, b); }
+#endif
 
 template <int V> struct ThCfg {
     static constexpr int VY = TH_TY + 2 * V;
     static constexpr int SU = TH_TY * TH_UX, SV = VY * TH_TX, SW = TH_TY * TH_TX;     // doubles per stage
     static constexpr int STAGE = SU + SV + SW;
-    static constexpr size_t bytes = (size_t)TH_NS * STAGE * sizeof(double) + 64;
-    static_assert((SU * 8) % 128 == 0 && (SV * 8) % 128 == 0 && (SW * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+    static constexpr size_t bytes = (size_t)TH_NS * STAGE * sizeof(real) + 64;
+    static_assert((SU * sizeof(real)) % 128 == 0 && (SV * sizeof(real)) % 128 == 0 && (SW * sizeof(real)) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
 template <int V>
 __global__ void __launch_bounds__(TH_NT, 2)
-theta_tma_kernel(const __grid_constant__ KConst c, double *__restrict__ theta, const double *__restrict__ wfield, int zchunk,
+theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, const real *__restrict__ wfield, int zchunk,
                  const __grid_constant__ ThetaMaps tm) {
     using G = ThCfg<V>;
-    extern __shared__ __align__(1024) double sth[];
+    extern __shared__ __align__(1024) real sth[];
     uint64_t *mbar_p = (uint64_t *)(sth + (size_t)TH_NS * G::STAGE);
     int *cnt = (int *)(mbar_p + TH_NS);
 
@@ -239,8 +245,8 @@ theta_tma_kernel(const __grid_constant__ KConst c, double *__restrict__ theta, c
     __syncthreads();
     // plane kk (u, v at kk; w at kk + V) -> ring stage st
     auto issue = [&](int kk, int st) {
-        const uint32_t mb = mb0 + 8 * st, su = s0 + (uint32_t)(st * G::STAGE * 8), sv = su + G::SU * 8, sw = sv + G::SV * 8;
-        th_mbar_expect_tx(mb, (uint32_t)(G::STAGE * sizeof(double)));
+        const uint32_t mb = mb0 + 8 * st, su = s0 + (uint32_t)(st * G::STAGE * sizeof(real)), sv = su + G::SU * (uint32_t)sizeof(real), sw = sv + G::SV * (uint32_t)sizeof(real);
+        th_mbar_expect_tx(mb, (uint32_t)(G::STAGE * sizeof(real)));
         th_tma_3d(su, &tm.u, mb, i0, j0 + L.gy, kk + L.gz);
         th_tma_3d(sv, &tm.v, mb, i0 + GX, j0 + L.gy - V, kk + L.gz);
         th_tma_3d(sw, &tm.w, mb, i0 + GX, j0 + L.gy, kk + V + L.gz);
@@ -249,43 +255,43 @@ theta_tma_kernel(const __grid_constant__ KConst c, double *__restrict__ theta, c
         for (int n = 0; n < TH_NS; n++) if (kfirst + n < klast) issue(kfirst + n, n);
     }
     // w of the 2V planes below the first one: this thread's four columns straight from global memory (16-byte aligned: i is even)
-    double2 wr[2][2 * V + 1];                                  // wr[r][V + l] = w of plane k+l, rows ty (r = 0) and ty + 8
+    real2 wr[2][2 * V + 1];                                  // wr[r][V + l] = w of plane k+l, rows ty (r = 0) and ty + 8
     const bool act[2] = {i < L.mx && j0 + ty < L.my, i < L.mx && j0 + ty + 8 < L.my};
 #pragma unroll
     for (int r = 0; r < 2; r++) {
-        const double *pw = wfield + L.idx(act[r] ? i : 0, act[r] ? j0 + ty + 8 * r : 0, kfirst - V);
+        const real *pw = wfield + L.idx(act[r] ? i : 0, act[r] ? j0 + ty + 8 * r : 0, kfirst - V);
 #pragma unroll
-        for (int m = 0; m < 2 * V; m++) wr[r][m + 1] = *reinterpret_cast<const double2 *>(pw + (size_t)m * L.plane);
+        for (int m = 0; m < 2 * V; m++) wr[r][m + 1] = *reinterpret_cast<const real2 *>(pw + (size_t)m * L.plane);
     }
     int st = 0; uint32_t par = 0;
     for (int k = kfirst; k < klast; k++) {
         th_mbar_wait(mb0 + 8 * st, par);
-        const double *su = sth + (size_t)st * G::STAGE, *sv = su + G::SU, *sw = sv + G::SV;
-        double2 th[2];
+        const real *su = sth + (size_t)st * G::STAGE, *sv = su + G::SU, *sw = sv + G::SV;
+        real2 th[2];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const int row = ty + 8 * r;
 #pragma unroll
             for (int m = 0; m < 2 * V; m++) wr[r][m] = wr[r][m + 1];
-            wr[r][2 * V] = *reinterpret_cast<const double2 *>(sw + row * TH_TX + 2 * lane);
+            wr[r][2 * V] = *reinterpret_cast<const real2 *>(sw + row * TH_TX + 2 * lane);
             // u: cells i-4 .. i+5 of the row as five aligned pairs; pt0 uses offsets -l..l around cell 0, pt1 around cell 1
-            const double2 *ur = reinterpret_cast<const double2 *>(su + row * TH_UX + GX + 2 * lane);
-            double uc[10];
+            const real2 *ur = reinterpret_cast<const real2 *>(su + row * TH_UX + GX + 2 * lane);
+            real uc[10];
 #pragma unroll
-            for (int m = 0; m < 5; m++) { const double2 t = ur[m - 2]; uc[2 * m] = t.x; uc[2 * m + 1] = t.y; }     // uc[4] = cell i, uc[5] = cell i+1
-            const double2 *vr = reinterpret_cast<const double2 *>(sv + (V + row) * TH_TX + 2 * lane);
-            double dudx0 = 0.0, dudx1 = 0.0, dvdy0 = 0.0, dvdy1 = 0.0, dwdz0 = 0.0, dwdz1 = 0.0;
+            for (int m = 0; m < 5; m++) { const real2 t = ur[m - 2]; uc[2 * m] = t.x; uc[2 * m + 1] = t.y; }     // uc[4] = cell i, uc[5] = cell i+1
+            const real2 *vr = reinterpret_cast<const real2 *>(sv + (V + row) * TH_TX + 2 * lane);
+            real dudx0 = 0.0, dudx1 = 0.0, dvdy0 = 0.0, dvdy1 = 0.0, dwdz0 = 0.0, dwdz1 = 0.0;
 #pragma unroll
             for (int l = 1; l <= V; l++) {
                 dudx0 = fma(c.c1[0][l], uc[4 + l] - uc[4 - l], dudx0);
                 dudx1 = fma(c.c1[0][l], uc[5 + l] - uc[5 - l], dudx1);
-                const double2 vp = vr[l * (TH_TX / 2)], vm = vr[-l * (TH_TX / 2)];
+                const real2 vp = vr[l * (TH_TX / 2)], vm = vr[-l * (TH_TX / 2)];
                 dvdy0 = fma(c.c1[1][l], vp.x - vm.x, dvdy0);
                 dvdy1 = fma(c.c1[1][l], vp.y - vm.y, dvdy1);
                 dwdz0 = fma(c.c1[2][l], wr[r][V + l].x - wr[r][V - l].x, dwdz0);
                 dwdz1 = fma(c.c1[2][l], wr[r][V + l].y - wr[r][V - l].y, dwdz1);
             }
-            th[r] = make_double2((dudx0 + dvdy0) + dwdz0, (dudx1 + dvdy1) + dwdz1);
+            th[r] = make_real2((dudx0 + dvdy0) + dwdz0, (dudx1 + dvdy1) + dwdz1);
         }
         // this warp is done with the stage: the last of the eight refills it with plane k + TH_NS
         __syncwarp();
@@ -301,7 +307,7 @@ theta_tma_kernel(const __grid_constant__ KConst c, double *__restrict__ theta, c
         for (int r = 0; r < 2; r++) {
             if (!act[r]) continue;
             const int j = j0 + ty + 8 * r;
-            double *pt = theta + L.idx(i, j, k);
+            real *pt = theta + L.idx(i, j, k);
             th_stg2(pt, th[r].x, th[r].y);
             if (j < V) th_stg2(pt + (size_t)L.my * L.px, th[r].x, th[r].y);
             if (j >= L.my - V) th_stg2(pt - (size_t)L.my * L.px, th[r].x, th[r].y);
@@ -320,7 +326,7 @@ int theta_tma_smem_bytes(int v) {
     switch (v) { case 1: return (int)ThCfg<1>::bytes; case 2: return (int)ThCfg<2>::bytes; case 3: return (int)ThCfg<3>::bytes; default: return (int)ThCfg<4>::bytes; }
 }
 // periodic x, uniform grid, no boundary layer, even mx; q = the padded state whose fields 1..3 the descriptors of `maps` describe
-void launch_theta_tma(const KConst &kc, const double *q, double *theta, const ThetaMaps &maps, cudaStream_t st) {
+void launch_theta_tma(const KConst &kc, const real *q, real *theta, const ThetaMaps &maps, cudaStream_t st) {
     const int gx = (kc.L.mx + TH_TX - 1) / TH_TX, gy = (kc.L.my + TH_TY - 1) / TH_TY;
     const int nk = kc.L.mz + 2 * kc.v;
     // z chunks: every chunk re-reads 2V planes of w; aim at a few waves of 148 SMs x 2 CTAs
@@ -329,7 +335,7 @@ void launch_theta_tma(const KConst &kc, const double *q, double *theta, const Th
     int zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);
-    const double *w = q + 3 * kc.L.vol;
+    const real *w = q + 3 * kc.L.vol;
 #define CUDNS_THETA_TMA_CASE(VV)                                                                    \
     {                                                                                               \
         opt_in_smem<theta_tma_kernel<VV>>((int)ThCfg<VV>::bytes);                                   \
@@ -344,7 +350,7 @@ void launch_theta_tma(const KConst &kc, const double *q, double *theta, const Th
 #undef CUDNS_THETA_TMA_CASE
 }
 
-void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaStream_t st) {
+void launch_theta_march(const KConst &kc, const real *q, real *theta, cudaStream_t st) {
     const int gx = (kc.L.mx + TXT - 1) / TXT, gy = (kc.L.my + TYT - 1) / TYT;
     const int nk = kc.L.mz + 2 * kc.v;
     // z chunks: every chunk pays a 2V-plane prologue of w; aim at a few waves of 148 SMs x 3 CTAs
@@ -356,7 +362,7 @@ void launch_theta_march(const KConst &kc, const double *q, double *theta, cudaSt
     const bool gen = !(kc.periodicX && !kc.nonUniformX && !kc.boundaryLayer);
 #define CUDNS_THETA_CASE(VV)                                                                        \
     {                                                                                               \
-        const size_t sm = (size_t)NST * (TYT * UX + (TYT + 2 * VV) * TXT + NTT) * sizeof(double);   \
+        const size_t sm = (size_t)NST * (TYT * UX + (TYT + 2 * VV) * TXT + NTT) * sizeof(real);   \
         opt_in_smem<theta_march_kernel<VV, true>>((int)sm);                                         \
         opt_in_smem<theta_march_kernel<VV, false>>((int)sm);                                        \
         if (gen) theta_march_kernel<VV, true><<<grid, NTT, sm, st>>>(kc, q, theta, zchunk);         \

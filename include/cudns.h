@@ -65,7 +65,11 @@ typedef struct cudns_params {
     int device;                /* CUDA device ordinal for this rank (setDevice, cuda_utils.cu:815) */
     int par2_enstrophy;        /* extension, default 0 = reference behaviour (calc_stress.cu:191-197 never writes par2 without forcing):
                                 * 1 makes cudns_advance record the mean square vorticity <w.w> of an unforced periodic box in par2 */
-    int reserved[4];
+    int precision;             /* `myprec` (globals.h:5-6) as a run-time value: 0 = double (default), 1 = float.  Device state, coefficient
+                                * tables and all kernel arithmetic run in that precision; host arrays crossing this ABI are double in both
+                                * (copyField casts, cuda_utils.cu:317-355), reduced scalars and statistics are accumulated in double.
+                                * float is built for the periodic / uniform / linear-viscosity set-ups with an even mx (Taylor-Green) */
+    int reserved[3];
 } cudns_params;
 
 typedef struct cudns_solver *cudns_handle;

@@ -89,6 +89,7 @@ def test_device_postprocess_reads_fields_and_writes_the_three_files(tmp_path):
     op = apply_cfg(ob.params_tgv(16, 3), CONFIGS[name])
     cp = copy_params(op, cd.Params()); cp.nranks = 1
     sol = cd.Solver(cp)
+    os.makedirs(os.path.join(tmp_path, "fields"))
     for n, st in enumerate(_snapshots(name)):
         for c, a in zip("ruvwe", st):
             cd.write_field(str(tmp_path), c, n + 1, a)
@@ -108,6 +109,7 @@ def test_driver_post_mode_is_the_reference_tool(tmp_path):
     import subprocess
     name = "chan_s2v2"
     cfg = CONFIGS[name]
+    os.makedirs(os.path.join(tmp_path, "fields"))
     for n, st in enumerate(_snapshots(name)):
         for c, a in zip("ruvwe", st):
             cd.write_field(str(tmp_path), c, n + 1, a)

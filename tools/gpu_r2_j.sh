@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_diagnostics.py -m gpu -q -x > gpurun_out/r2j_pytest.log 2>&1; tail -3 gpurun_out/r2j_pytest.log
-timeout 300 python tools/quick_perf.py 512,4,4 512,4,4,rk4 512,4,4,kutta 2>&1 | grep -v advance | tee gpurun_out/r2j_quick_perf.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_diagnostics.py tests/test_post.py -m gpu -q -x > gpurun_out/r2j_pytest.log 2>&1; tail -3 gpurun_out/r2j_pytest.log
+CUDNS_DUO=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2j_pytest_duo.log 2>&1; tail -3 gpurun_out/r2j_pytest_duo.log
+(echo "== fast (gen 4) ls3"; timeout 300 python tools/quick_perf.py 512,4,4 2>&1 | grep -v advance
+echo "== duo"; CUDNS_DUO=1 timeout 300 python tools/quick_perf.py 512,4,4 512,4,4,rk4 512,4,4,kutta 2>&1 | grep -v advance) | tee gpurun_out/r2j_quick_perf.log
+export CUDNS_DUO=1
 bash tools/gpu_variants.sh "512,4,4 512,4,4,rk4" head pf0 pf4 slot32
 cp gpurun_out/variants.log gpurun_out/r2j_variants.log
 ncu --set full --clock-control none --import-source on -k regex:stage_kernel -s 6 -c 1 -f -o gpurun_out/r2j_duo5_full python tools/quick_perf.py 512,4,4 > gpurun_out/r2j_duo5_full.log 2>&1
