@@ -29,6 +29,10 @@ def params(nranks, r):
         p = cd.params_tgv(n, 3, stencilVisc=2, viscexp=0.7)
     elif case == "kutta":
         p = cd.params_tgv(n, 4, lowStorage=0)
+    elif case == "tgv_f32":
+        p = cd.params_tgv(n, 4, precision=1)
+    elif case == "rk4_f32":
+        p = cd.params_tgv(n, 4, precision=1, lowStorage=0, rk4=1)
     else:
         raise SystemExit("unknown case")
     p.nranks = nranks; p.rank = r; p.device = local
@@ -60,7 +64,7 @@ if rank == 0:
     ref = cd.Solver(params(1, 0), grid); ref.set_state(full); ref.advance(steps); single = np.stack(ref.get_state()); ref.close()
     cons = lambda s: [s[0], s[0] * s[1], s[0] * s[2], s[0] * s[3], s[4]]
     errs = [float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) for a, b in zip(cons(multi), cons(single))]
-    stages = 3
+    stages = 4 if case.startswith("rk4") else 3
     print("mgpu_check n=%d ranks=%d mode=%s case=%s steps=%d: max rel diff vs single GPU %s | %.3f ms/step -> %.2f Gpts*stage/s | stage kernels %s peer=%s"
           % (n, world, mode, case, steps, ["%.1e" % e for e in errs], t.item() / steps, n ** 3 * stages * steps / (t.item() * 1e-3) / 1e9, prof,
              getattr(sol, "peer_transport", None)), flush=True)
