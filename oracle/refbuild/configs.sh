@@ -36,3 +36,5 @@ PERF[perf256_n40]="$P256 nsteps=40"
 P512="${P256//256/512}"
 PERF[perf512_n5]="$P512 nsteps=5"
 PERF[perf512_n15]="$P512 nsteps=15"
+# (a longer run: the difference of two whole-run wall clocks carries ~0.5 s of set-up noise, 10 steps of 0.3 s drown in it)
+PERF[perf512_n45]="$P512 nsteps=45"
