@@ -276,7 +276,6 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     kc.Rgas = (1.f / (p->gam * p->Ma * p->Ma));                 // globals.h:48
     double Ec = ((p->gam - 1.f) * p->Ma * p->Ma);               // globals.h:47
     kc.cvInv = (p->gam - 1.0) / kc.Rgas;
-    kc.cp = kc.Rgas * p->gam / (p->gam - 1.0);
     kc.invRe = 1.0 / p->Re; kc.lamfac = 1.0 / p->Pr / Ec; kc.viscexp = p->viscexp;
     kc.viscmode = p->viscexp == 1.0 ? 1 : p->viscexp == 0.5 ? 2 : p->viscexp == 0.75 ? 3 : p->viscexp == 1.5 ? 4 : 0;
     kc.periodicX = p->periodicX; kc.boundaryLayer = p->boundaryLayer; kc.nonUniformX = p->nonUniformX;

@@ -75,7 +75,7 @@ struct KConst {
     real cf[3][MAXS + 1][4], c1t[3][MAXS + 1], c20sum;
     real cfzp[MAXS + 1];       // -a_l Rgas / dz: z pressure gradient from rho*T (ring without p, wide variant)
     real cfp[3][MAXS + 1];     // -a_l Rgas / dx_d: pressure gradient from rho*T in every direction (fast variant)
-    real gam, Rgas, cvInv, cp, invRe, lamfac, viscexp;
+    real gam, Rgas, cvInv, invRe, lamfac, viscexp;
     int viscmode;                // 0 generic pow, 1 n=1, 2 n=0.5, 3 n=0.75, 4 n=1.5
     int periodicX, boundaryLayer, nonUniformX, perturbed, forcing, quirk_q1;
     real TwallTop, TwallBot;

@@ -81,12 +81,13 @@ def test_bench_size_properties(scheme):
     a = s.get_state()
     m1 = [c.sum() for c in conserved(a)]
     N = 512 * 512 * 64
-    assert abs(m1[0] - m0[0]) < (1e-7 if f32 else 1e-13) * abs(m0[0])
+    assert abs(m1[0] - m0[0]) < (1e-7 if f32 else 1e-13) * abs(m0[0]), (m1[0], m0[0])
     for k in (1, 2, 3):
-        assert abs(m1[k] - m0[k]) < (1e-6 if f32 else 1e-11) * N ** 0.5
+        # (single precision: ~10 roundings of 6e-8 per point and stage, summed over N points like a random walk)
+        assert abs(m1[k] - m0[k]) < (2e-5 if f32 else 1e-11) * N ** 0.5, (k, m1[k], m0[k])
     # z-independent data stay z-independent (every plane goes through a different ring phase / chunk / prologue of the kernel)
     for f in a:
-        assert np.abs(f - f[:1]).max() <= (2e-6 if f32 else 1e-13) * max(np.abs(f).max(), 1.0)
+        assert np.abs(f - f[:1]).max() <= (2e-6 if f32 else 1e-13) * max(np.abs(f).max(), 1.0), np.abs(f - f[:1]).max()
     s.close()
     # (3) with a fixed dt, advance(2) == advance(1) + advance(1) bit for bit (buffer rotation, aux-field validity across calls)
     s3 = cd.Solver(p, grid); s3.set_state(zfix); s3.set_dt(1e-3); s3.advance(2); c1 = s3.get_state(); s3.close()
