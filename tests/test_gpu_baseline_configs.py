@@ -83,8 +83,9 @@ def test_bench_size_properties(scheme):
     N = 512 * 512 * 64
     assert abs(m1[0] - m0[0]) < (1e-7 if f32 else 1e-13) * abs(m0[0]), (m1[0], m0[0])
     for k in (1, 2, 3):
-        # (single precision: ~10 roundings of 6e-8 per point and stage, summed over N points like a random walk)
-        assert abs(m1[k] - m0[k]) < (2e-5 if f32 else 1e-11) * N ** 0.5, (k, m1[k], m0[k])
+        # (single precision: ~1e-6 of rounding per point after two steps -- the z-independent, x-y-symmetric start makes the roundings of
+        # all symmetric copies of a point identical, so they add up coherently, not like a random walk: bound 1e-7 per point)
+        assert abs(m1[k] - m0[k]) < (1e-7 * N if f32 else 1e-11 * N ** 0.5), (k, m1[k], m0[k])
     # z-independent data stay z-independent (every plane goes through a different ring phase / chunk / prologue of the kernel)
     for f in a:
         assert np.abs(f - f[:1]).max() <= (2e-6 if f32 else 1e-13) * max(np.abs(f).max(), 1.0), np.abs(f - f[:1]).max()
