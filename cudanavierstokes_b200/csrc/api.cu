@@ -744,10 +744,13 @@ int cudns_calc_rhs(cudns_handle S, double *rhs_r, double *rhs_u, double *rhs_v, 
     std::vector<real> hbuf(sizeof(real) == sizeof(double) ? 0 : S->N);          // single precision: widened on the host
     for (int f = 0; f < 5; f++) {
         if (!dst[f]) continue;
-        if (sizeof(real) == sizeof(double)) { CK(cudaMemcpyAsync(dst[f], tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st)); continue; }
-        CK(cudaMemcpyAsync(hbuf.data(), tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st));
-        CK(cudaStreamSynchronize(S->st));
-        for (size_t n = 0; n < S->N; n++) dst[f][n] = (double)hbuf[n];
+        if constexpr (!kF32) {
+            CK(cudaMemcpyAsync(dst[f], tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st));
+        } else {
+            CK(cudaMemcpyAsync(hbuf.data(), tmp + f * S->N, S->N * sizeof(real), cudaMemcpyDeviceToHost, S->st));
+            CK(cudaStreamSynchronize(S->st));
+            for (size_t n = 0; n < S->N; n++) dst[f][n] = (double)hbuf[n];
+        }
     }
     CK(cudaStreamSynchronize(S->st));
     cudaFree(tmp);

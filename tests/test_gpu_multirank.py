@@ -24,9 +24,11 @@ class _DevMem:
         self.__cuda_array_interface__ = {"shape": (ndoubles,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
 
 
-def _run_two_ranks(p_of, full, grid, steps, peer, sponge=None, scalars=None):
+def _run_two_ranks(p_of, full, grid, steps, peer, sponge=None, scalars=None, after=None, extras=None):
     """advance the same problem as 2 slabs in two threads; returns the gathered state.  sponge = (sigma_x, sigma_z, ref5) GLOBAL
-    tables (each rank takes its slab); scalars: optional list that receives rank 0's dt / dpdz / time after the run"""
+    tables (each rank takes its slab); scalars: optional list that receives rank 0's dt / dpdz / time after the run; after(solver,
+    rank) runs on every rank's thread after the steps (collective calls: both ranks make them in the same order), its results land
+    in extras[rank]"""
     import torch
     nr = 2
     sols = [cd.Solver(p_of(nr, r), grid) for r in range(nr)]
@@ -79,6 +81,8 @@ def _run_two_ranks(p_of, full, grid, steps, peer, sponge=None, scalars=None):
             out[r] = sols[r].get_state()
             if scalars is not None and r == 0:
                 scalars.append(sols[r].scalars())
+            if after is not None:
+                extras[r] = after(sols[r], r)
         except Exception as e:       # noqa: BLE001
             errors.append(e); bar.abort()
 
@@ -166,6 +170,57 @@ def test_two_slabs_boundary_layer(peer):
     multi = _run_two_ranks(p_of, ic, grid, 12, peer, sponge=(sx, sz, refq))
     errs = [relerr(a, b, floor=1e-30) for a, b in zip(conserved(multi), conserved(single))]
     assert max(errs) < 1e-13, errs
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("prec", [0, 1])
+def test_two_slabs_enstrophy_and_single_precision(prec):
+    """the dissipation measure <w.w> is a cross-rank SUM; precision = 1: the float copy of the device side through the same slab
+    logic (ghost stores into the neighbour's block, hand-shake, scalar reductions in double)"""
+    def p_of(nranks, rank):
+        p = cd.params_tgv(32, 3, mz=48, precision=prec, checkBulk=2, par2_enstrophy=1)
+        p.nranks = nranks; p.rank = rank; p.device = 0
+        return p
+    p1 = p_of(1, 0)
+    grid = cd.init_grid(p1)
+    full = cd.init_chit(p1, grid)
+    ref = cd.Solver(p1, grid); ref.set_state(full); t1, a1, b1 = ref.advance(6); single = ref.get_state(); e1 = ref.enstrophy(); ref.close()
+    extras = [None, None]
+    multi = _run_two_ranks(p_of, full, grid, 6, True, after=lambda sol, r: sol.enstrophy(), extras=extras)
+    errs = [relerr(a, b) for a, b in zip(conserved(multi), conserved(single))]
+    assert max(errs) < 1e-13, errs
+    assert abs(extras[0] - e1) <= 1e-13 * e1 and extras[0] == extras[1]
+    assert np.isfinite(b1[::2]).all() and np.isnan(b1[1::2]).all()         # par2 = <w.w> at the checkBulk steps only
+
+
+@pytest.mark.timeout(300)
+def test_two_slabs_post_statistics():
+    """postproc/post.cpp as device reductions across two slabs (partial sums per rank, cross-rank SUM through the callback): equal to
+    one slab and to the reference's own tool"""
+    import oracle_binding  # noqa: F401  (tests/ on the path)
+    from common import load_golden
+    from ref_cases import GOLDEN
+    cfg, p_of = _golden_params("chan_s3v2")
+    g = load_golden("chan_s3v2")
+    snaps = [list(g["file0"]), list(g["file2"])]
+    p1 = p_of(1, 0)
+    grid = cd.init_grid(p1)
+    ref = cd.Solver(p1, grid); one = ref.post_stats(snaps); ref.close()
+
+    def stats(sol, r):
+        mzl = sol.mzl
+        return sol.post_stats([[a[r * mzl:(r + 1) * mzl] for a in st] for st in snaps])
+    extras = [None, None]
+    _run_two_ranks(p_of, snaps[0], grid, 0, False, after=stats, extras=extras)
+    for key in ("mean", "fluc", "bulk"):
+        scale = np.abs(one[key]).max(axis=-1, keepdims=True) if key != "bulk" else np.abs(one[key])
+        if key == "fluc":
+            scale = np.maximum(scale, 1e-3 * np.abs(one["mean"]).max(axis=-1, keepdims=True) ** 2)
+        assert (np.abs(extras[0][key] - one[key]) <= 1e-12 * np.maximum(scale, 1e-300)).all(), key
+        assert np.array_equal(extras[0][key], extras[1][key])                 # every rank holds the reduced result
+    assert abs(extras[0]["Ret"] - one["Ret"]) <= 1e-12 * one["Ret"]
+    tool = np.load(os.path.join(GOLDEN, "ref_post_chan_s3v2.npz"))
+    assert abs(extras[0]["Ret"] - float(tool["Ret"])) <= 1e-6
 
 
 @pytest.mark.timeout(600)
