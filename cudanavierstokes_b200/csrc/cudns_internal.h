@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -210,6 +211,27 @@ inline void opt_in_smem(int bytes) {
 }
 
 bool rhs_stage_supported(int s, int v);
+
+// z chunks of a marching stage kernel: `cols` tiles, each split into n chunks of mz/n planes.  Every chunk re-primes its ring (2s
+// planes of loads, worth ~0.8 s planes of work) and the grid runs in waves of `resident` CTAs (148 SMs x CTAs per SM); with w =
+// CTAs / resident the run takes max(ceil(w), w + 1) chunk times -- whole waves when every CTA takes the same time, about one CTA
+// time of tail otherwise (wall tiles, unequal clocks).  Fitted to a sweep on one B200 (profiles/r02_zchunk_sweep.log: channel
+// 160x192x192 0.59 -> 0.53 ms per stage, boundary layer and Taylor-Green 512^3 unchanged within 1.5 %).  Any n is allowed, not only
+// powers of two; chunks stay >= 16 planes (the bandwidth-bound dilatation pass: >= 64, its tail wave costs less).
+inline int pick_zchunks(int cols, int mz, int s, int resident, int min_chunk = 16) {
+    if (const char *e = getenv("CUDNS_ZCHUNKS")) { const int n = atoi(e); if (n >= 1 && mz / n >= 2 * s + 1) return n; }   // experiments
+    int best = 1; double best_cost = 1e300;
+    for (int n = 1; n <= 128; n++) {
+        const int zc = (mz + n - 1) / n;
+        if (n > 1 && zc < min_chunk) break;
+        const int nn = (mz + zc - 1) / zc;                         // chunks this plane count really gives
+        const long ctas = (long)cols * nn;
+        const double w = (double)ctas / resident, waves = (double)((ctas + resident - 1) / resident);
+        const double cost = (waves > w + 1.0 ? waves : w + 1.0) * (zc + 0.8 * s);
+        if (cost < best_cost * 0.995) { best_cost = cost; best = nn; }
+    }
+    return best;
+}
 
 
 }  // namespace cudns

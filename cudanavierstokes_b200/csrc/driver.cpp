@@ -10,7 +10,7 @@
 // par2 column), post=<first>:<last> (no time stepping: the reference's post-processing tool postproc/post.cpp over the saved
 // fields/<c>.<first..last>.bin of outdir -> mean.txt, fluc.txt, bulk.txt there).
 // Outputs, in outdir, with the reference's names and formats: Grid.txt, fields/{x,y,z}.bin, fields/{r,u,v,w,e}.<%07d>.bin,
-// solution.txt, prof.txt (+ fields.xmf).  --dry-run stops before the GPU is touched (grid, initial condition, file 0).
+// solution.txt, prof.txt, inProf.txt / inRef.txt (boundary layer) (+ fields.xmf).  --dry-run stops before the GPU is touched (grid, initial condition, file 0).
 #include <cudns.h>
 
 #include <chrono>
@@ -148,6 +148,21 @@ int main(int argc, char **argv) {
         CK(cudns_build_sponge(&P, x.data(), z.data(), bx.data() + 1, br.data() + 1, bu.data() + 1, bw.data() + 1, n - 1, sigx.data(), sigz.data(),
                               ref5.data(), fresh ? r.data() : nullptr, fresh ? u.data() : nullptr, fresh ? v.data() : nullptr,
                               fresh ? w.data() : nullptr, fresh ? e.data() : nullptr));
+        {   // the two text files calculateSponge leaves behind (sponge.cu:178-182,196-200): the similarity profiles as read, and the
+            // inflow reference state (plane k = 0 of the reference tables = of a fresh initial field)
+            FILE *fw = std::fopen((outdir + "/inProf.txt").c_str(), "w+");
+            if (!fw) die("cannot write inProf.txt");
+            for (int i = 0; i < n; i++) std::fprintf(fw, "%le %le %le %le %le\n", bx[i], br[i], bu[i], bw[i], be[i]);
+            std::fclose(fw);
+            fw = std::fopen((outdir + "/inRef.txt").c_str(), "w+");
+            if (!fw) die("cannot write inRef.txt");
+            const size_t nt = (size_t)P.mx * P.mz;                       // ref5 = (rho, rho u, rho v, rho w, rho E) tables [mx*mz], index i + k*mx
+            for (int i = 0; i < P.mx; i++) {
+                const double rr = ref5[i];
+                std::fprintf(fw, "%le %le %le %le %le\n", x[i], rr, ref5[nt + i] / rr, ref5[3 * nt + i] / rr, ref5[4 * nt + i]);
+            }
+            std::fclose(fw);
+        }
     } else if (fresh) {
         if (P.forcing) CK(cudns_init_channel(&P, x.data(), y.data(), z.data(), r.data(), u.data(), v.data(), w.data(), e.data()));
         else CK(cudns_init_chit(&P, x.data(), y.data(), z.data(), r.data(), u.data(), v.data(), w.data(), e.data()));

@@ -436,8 +436,7 @@ static void launch_t(const KConst &kc, const StagePtrs &p, const StageCoef &c, c
     const int gx = (kc.L.mx + TX - 1) / TX, gy = (kc.L.my + TY - 1) / TY;
     // z chunks: every chunk pays a 2S-plane prologue, so keep them >= 32 planes; more chunks smooth the tail over the SMs
     const int cols = gx * gy, resident = 148 * (TY == 16 ? 1 : 2);
-    int nzc = 1;
-    while (cols * nzc < resident * 16 && kc.L.mz / (nzc * 2) >= 32) nzc *= 2;
+    int nzc = pick_zchunks(cols, kc.L.mz, S, resident);
     int zchunk = (kc.L.mz + nzc - 1) / nzc;
     nzc = (kc.L.mz + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);

@@ -16,6 +16,7 @@
 //     the z extrapolation of the boundary layer (BCzderVel, boundary_condition_z.h:34-40) is applied on the few
 //     planes next to the global z boundaries by a slow path that reads global memory directly.
 #include "cudns_internal.h"
+#include <cstdlib>
 
 namespace cudns {
 namespace {
@@ -329,9 +330,10 @@ int theta_tma_smem_bytes(int v) {
 void launch_theta_tma(const KConst &kc, const real *q, real *theta, const ThetaMaps &maps, cudaStream_t st) {
     const int gx = (kc.L.mx + TH_TX - 1) / TH_TX, gy = (kc.L.my + TH_TY - 1) / TH_TY;
     const int nk = kc.L.mz + 2 * kc.v;
-    // z chunks: every chunk re-reads 2V planes of w; aim at a few waves of 148 SMs x 2 CTAs
-    int nzc = 1;
-    while (gx * gy * nzc < 148 * 2 * 3 && nk / (nzc * 2) >= 32) nzc *= 2;
+    // z chunks: every chunk re-reads 2V planes of w; whole waves of 148 SMs x 2 CTAs (512^3: 8 chunks = 6.9 waves, 0.70 ms; the 4
+    // chunks = 3.5 waves of the first version: 0.74 ms, profiles/r02_zchunk_sweep.log)
+    int nzc = pick_zchunks(gx * gy, nk, kc.v, 148 * 2, 64);
+    if (const char *e = getenv("CUDNS_THETA_ZCHUNKS")) { const int n = atoi(e); if (n >= 1 && nk / n >= 8) nzc = n; }      // experiments
     int zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);

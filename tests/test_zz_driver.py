@@ -42,6 +42,12 @@ def test_config_file_and_errors(tmp_path):
     r = _run([str(cfg), "--dry-run"])
     assert r.returncode == 0 and "case blayer  grid 48 x 16 x 192" in r.stdout, r.stderr
     assert (tmp_path / "bl" / "fields" / "r.0000000.bin").stat().st_size == 48 * 16 * 192 * 8
+    # the text files calculateSponge leaves behind (sponge.cu:178-200): similarity profiles as read, inflow reference state
+    prof = np.loadtxt(tmp_path / "bl" / "inProf.txt"); ref = np.loadtxt(tmp_path / "bl" / "inRef.txt")
+    assert prof.shape == (1000, 5) and ref.shape == (48, 5)
+    r0 = np.fromfile(tmp_path / "bl" / "fields" / "r.0000000.bin").reshape(192, 16, 48)[0, 0]
+    w0 = np.fromfile(tmp_path / "bl" / "fields" / "w.0000000.bin").reshape(192, 16, 48)[0, 0]
+    assert np.allclose(ref[:, 1], r0, rtol=2e-6) and np.allclose(ref[:, 3], w0, rtol=2e-6, atol=1e-12)      # "%le": 7 digits
     r = _run(["nosuchkey=3", "--dry-run"])
     assert r.returncode != 0 and "unknown key" in r.stderr
     r = _run(["case=tgv", "mx=16", "my=16", "mz=16", "stencilSize=2", "stencilVisc=3", "outdir=%s" % (tmp_path / "bad")])
