@@ -34,7 +34,7 @@ EXPORTS = [
     "cudns_write_xdmf", "cudns_write_fields_async", "cudns_io_wait", "cudns_read_fields",
     "cudns_calc_profiles", "cudns_calc_retau", "cudns_blasius_profiles", "cudns_calc_enstrophy",
     "cudns_stats_begin", "cudns_stats_add_mean", "cudns_stats_finish_mean", "cudns_stats_add_fluc", "cudns_stats_get",
-    "cudns_stats_write", "cudns_postprocess",
+    "cudns_stats_write", "cudns_postprocess", "cudns_team_create", "cudns_team_destroy",
 ]
 
 
@@ -149,6 +149,8 @@ def lib():
     L.cudns_stats_get.argtypes = [H, dp, dp, dp, dp, dp]
     L.cudns_stats_write.argtypes = [C.c_char_p, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double]
     L.cudns_postprocess.argtypes = [H, C.c_char_p, C.c_int, C.c_int, dp, C.c_char_p]
+    L.cudns_team_create.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_void_p)]
+    L.cudns_team_destroy.argtypes = [C.c_void_p]
     L.cudns_io_wait.argtypes = [H, C.POINTER(C.c_uint64)]
     L.cudns_read_fields.argtypes = [H, C.c_char_p, C.c_int]
     L.cudns_write_xdmf.argtypes = [C.c_char_p, C.c_int, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_char_p]

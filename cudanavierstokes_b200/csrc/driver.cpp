@@ -1,12 +1,12 @@
 // cudns_run -- host driver on top of the C ABI (include/cudns.h): what main.cpp:27-90 + solverWrapper (cuda_main.cu:267-327) do in
-// the reference, with run-time configuration instead of compile-time globals.h.  One process, one GPU (multi-GPU runs are driven
-// through cudanavierstokes_b200/dist.py, which owns the rank bootstrap).
+// the reference, with run-time configuration instead of compile-time globals.h.  One process; ngpus=N runs N z-slabs on N GPUs of
+// the box from N host threads (multi-process runs are driven through cudanavierstokes_b200/dist.py, which owns the rank bootstrap).
 //
 //   cudns_run [config-file] [key=value ...] [--dry-run]
 //
 // keys: case=tgv|channel|blayer (presets of python-utils/CompNavierStokes.py, globals/channel.h, src/globals.h), every field of
 // cudns_params by name (mx, stencilSize, Re, ...), nsteps, nfiles, restartFile (-1: fresh start), outdir (default "."),
-// blasius=internal|<dir with {x,r,u,w,e}Prof.bin>, async_io=0|1, xdmf=0|1, par2_enstrophy=0|1 (Taylor-Green dissipation history in the
+// blasius=internal|<dir with {x,r,u,w,e}Prof.bin>, async_io=0|1, xdmf=0|1, ngpus=N (z-slabs on devices device..device+N-1 of this box; samedevice=1: all on one, for tests), par2_enstrophy=0|1 (Taylor-Green dissipation history in the
 // par2 column), post=<first>:<last> (no time stepping: the reference's post-processing tool postproc/post.cpp over the saved
 // fields/<c>.<first..last>.bin of outdir -> mean.txt, fluc.txt, bulk.txt there).
 // Outputs, in outdir, with the reference's names and formats: Grid.txt, fields/{x,y,z}.bin, fields/{r,u,v,w,e}.<%07d>.bin,
@@ -19,9 +19,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
+#include <mutex>
 #include <string>
 #include <sys/stat.h>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -76,6 +79,27 @@ void write_bin(const std::string &path, const double *v, size_t n) {
     std::fclose(f);
 }
 
+
+// ---- the slabs of a multi-GPU run inside one process: one host thread per GPU (the library's cudns_team wires the solvers together)
+struct Team {
+    int n;
+    std::mutex m; std::condition_variable cv; int waiting = 0; unsigned long gen = 0; uint64_t written = 0;
+    explicit Team(int n_) : n(n_) {}
+    void barrier() {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned long g = gen;
+        if (++waiting == n) { waiting = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+    void add_written(uint64_t k) { std::lock_guard<std::mutex> lk(m); written += k; }
+    template <class F> void run(F &&f) {
+        if (n == 1) { f(0); return; }
+        std::vector<std::thread> th;
+        for (int r = 0; r < n; r++) th.emplace_back([&, r] { f(r); });
+        for (auto &t : th) t.join();
+    }
+};
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -94,6 +118,9 @@ int main(int argc, char **argv) {
     const std::string outdir = take("outdir", "."), blasius = take("blasius", "internal");
     const bool async_io = std::atoi(take("async_io", "1").c_str()) != 0, xdmf = std::atoi(take("xdmf", "1").c_str()) != 0;
     const std::string post = take("post", "");
+    const int ngpus = std::atoi(take("ngpus", "1").c_str());
+    const bool samedevice = std::atoi(take("samedevice", "0").c_str()) != 0;      // testing aid: all slabs on ONE device
+    if (ngpus < 1 || ngpus > 64) die("ngpus must be in 1..64");
     if (nsteps < 2 || nfiles < 1) die("nsteps must be >= 2 and nfiles >= 1");
 
     cudns_params P;
@@ -114,7 +141,7 @@ int main(int argc, char **argv) {
     }
     if (kv.count("stencilSize") && !kv.count("stencilVisc") && cas == "tgv") P.stencilVisc = P.stencilSize;
     if (!kv.count("omega1")) P.omega1 = P.Re * 121.e-6;                  // perturbation.h:20 derives it from Re
-    P.nranks = 1; P.rank = 0;
+    P.nranks = 1; P.rank = 0;                                            // (host set-up below works on the global grid)
 
     // ---- initGrid (init.cpp:32-92): grid, Grid.txt, fields/{x,y,z}.bin
     ::mkdir(outdir.c_str(), 0755); ::mkdir((outdir + "/fields").c_str(), 0755);
@@ -181,25 +208,44 @@ int main(int argc, char **argv) {
         return 0;
     }
 
-    // ---- setDevice + setGPUParameters + initSolver + copyField(0) (main.cpp:62-66)
-    cudns_handle H;
-    CK(cudns_create(&P, x.data(), xp.data(), xpp.data(), &H));
+    // ---- setDevice + setGPUParameters + initSolver + copyField(0) (main.cpp:62-66), one solver per GPU.  ngpus > 1: z-slabs inside
+    // this one process (one host thread per GPU, the role of the reference's MPI ranks): the slabs' state blocks are mapped into each
+    // other (cudns_halo_connect, same-process branch: peer access) so that the stage kernel stores its boundary planes straight into the
+    // neighbours' ghost planes over NVLink; scalar reductions and the one-off ghost fill of copyField(0) go through the two callbacks below
+    P.nranks = ngpus;
+    if (P.mz % ngpus) die("mz must be divisible by ngpus");
+    const int mzl = P.mz / ngpus;
+    const size_t Nl = (size_t)P.mx * P.my * mzl;
+    Team team(ngpus);
+    std::vector<cudns_handle> H(ngpus, nullptr);
+    for (int rk = 0; rk < ngpus; rk++) {
+        cudns_params Pr = P; Pr.rank = rk; Pr.device = samedevice ? P.device : P.device + rk;
+        CK(cudns_create(&Pr, x.data(), xp.data(), xpp.data(), &H[rk]));
+    }
+    cudns_team_handle group = nullptr;
+    if (ngpus > 1) CK(cudns_team_create(H.data(), ngpus, &group));
     if (!post.empty()) {               // postproc/post.cpp:126-199 instead of the time loop
         int first = 0, last = 0;
         if (std::sscanf(post.c_str(), "%d:%d", &first, &last) != 2) die("post=<first>:<last> expected");
         std::printf("Fields to postprocess :  %d -> %d\n", first, last);
-        CK(cudns_postprocess(H, outdir.c_str(), first, last, x.data(), outdir.c_str()));
-        CK(cudns_destroy(H));
+        team.run([&](int rk) { CK(cudns_postprocess(H[rk], outdir.c_str(), first, last, x.data(), outdir.c_str())); });
+        for (int rk = 0; rk < ngpus; rk++) CK(cudns_destroy(H[rk]));
+        if (group) CK(cudns_team_destroy(group));
         std::printf("cudns_run: wrote mean.txt, fluc.txt, bulk.txt\n");
         return 0;
     }
-    if (P.boundaryLayer) CK(cudns_set_sponge(H, sigx.data(), sigz.data(), ref5.data()));
-    if (fresh) CK(cudns_set_state(H, r.data(), u.data(), v.data(), w.data(), e.data()));
-    else CK(cudns_read_fields(H, outdir.c_str(), restartFile));
-    std::vector<double>().swap(r); std::vector<double>().swap(u); std::vector<double>().swap(v); std::vector<double>().swap(w); std::vector<double>().swap(e);
-    auto write_prof = [&]() {              // calcAvgChan (init.cpp:150-208): prof.txt is rewritten at every output
+    // this rank's slab of the sponge tables: ref5 is [5][mz][mx], sigma_z is [mz]
+    auto set_sponge = [&](int rk) {
+        if (!P.boundaryLayer) return;
+        std::vector<double> rf(5 * (size_t)P.mx * mzl);
+        for (int f = 0; f < 5; f++)
+            std::memcpy(rf.data() + (size_t)f * P.mx * mzl, ref5.data() + (size_t)f * P.mx * P.mz + (size_t)rk * P.mx * mzl, sizeof(double) * P.mx * mzl);
+        CK(cudns_set_sponge(H[rk], sigx.data(), sigz.data() + (size_t)rk * mzl, rf.data()));
+    };
+    auto write_prof = [&](int rk) {        // calcAvgChan (init.cpp:150-208): prof.txt is rewritten at every output (a collective call)
         std::vector<double> prof(10 * (size_t)P.mx);
-        CK(cudns_calc_profiles(H, prof.data()));
+        CK(cudns_calc_profiles(H[rk], prof.data()));
+        if (rk != 0) return;
         FILE *fp = std::fopen((outdir + "/prof.txt").c_str(), "w+");
         if (!fp) die("cannot write prof.txt");
         for (int i = 0; i < P.mx; i++) {
@@ -209,50 +255,62 @@ int main(int argc, char **argv) {
         }
         std::fclose(fp);
     };
-    {   // calcdt + printRes + calcAvgChan of the initial field (main.cpp:57-60)
-        double dt0 = 0.0, ret = 0.0;
-        CK(cudns_calc_dt(H, &dt0));
-        std::printf("the initial dt is : %lf\n", dt0);
-        if (!P.periodicX) { CK(cudns_calc_retau(H, &ret)); std::printf("The average friction Reynolds number is: \t %lf\n", ret); }
-        write_prof();
-    }
     std::vector<int> saved;
-    if (fresh) { CK(cudns_write_fields_async(H, outdir.c_str(), 0)); if (!async_io) CK(cudns_io_wait(H, nullptr)); saved.push_back(0); }
-
-    // ---- solverWrapper (cuda_main.cu:267-327)
     const int start = fresh ? 0 : restartFile;
     FILE *sol = std::fopen((outdir + "/solution.txt").c_str(), "w+");
     if (!sol) die("cannot write solution.txt");
-    std::vector<double> htime(nsteps), hpar1(nsteps), hpar2(nsteps);
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int file = start + 1; file < nfiles + start + 1; file++) {
-        std::fill(hpar1.begin(), hpar1.end(), 0.0); std::fill(hpar2.begin(), hpar2.end(), 0.0);
-        CK(cudns_advance(H, nsteps, htime.data(), hpar1.data(), hpar2.data()));
-        CK(cudns_write_fields_async(H, outdir.c_str(), file));         // copyField(1) + writeField(file) without stalling the next file
-        if (!async_io) CK(cudns_io_wait(H, nullptr));
-        saved.push_back(file);
-        write_prof();
-        // par1 / par2 are refreshed every checkBulk steps: report the last refreshed entry like the reference's device arrays hold it
-        int last = ((nsteps - 1) / P.checkBulk) * P.checkBulk;
-        std::printf("file number: %d  \t step: %d  \t time: %lf  \t kin: %le  \t energy: %le\n", file, file * nsteps, htime[nsteps - 1], hpar1[last], hpar2[last]);
-        for (int t = 0; t < nsteps - 1; t += P.checkCFLcondition)
-            std::fprintf(sol, "%d %lf %lf %lf %lf\n", file * (t + 1), htime[t], hpar1[t], hpar2[t], htime[t + 1] - htime[t]);
-        std::fflush(sol);
-    }
-    std::fclose(sol);
+    std::chrono::steady_clock::time_point t0;
     uint64_t nwritten = 0;
-    CK(cudns_io_wait(H, &nwritten));
+    team.run([&](int rk) {
+        set_sponge(rk);
+        if (fresh) CK(cudns_set_state(H[rk], r.data() + rk * Nl, u.data() + rk * Nl, v.data() + rk * Nl, w.data() + rk * Nl, e.data() + rk * Nl));
+        else CK(cudns_read_fields(H[rk], outdir.c_str(), restartFile));
+        {   // calcdt + printRes + calcAvgChan of the initial field (main.cpp:57-60)
+            double dt0 = 0.0, ret = 0.0;
+            CK(cudns_calc_dt(H[rk], &dt0));
+            if (rk == 0) std::printf("the initial dt is : %lf\n", dt0);
+            if (!P.periodicX) { CK(cudns_calc_retau(H[rk], &ret)); if (rk == 0) std::printf("The average friction Reynolds number is: \t %lf\n", ret); }
+            write_prof(rk);
+        }
+        if (fresh) { CK(cudns_write_fields_async(H[rk], outdir.c_str(), 0)); if (!async_io) CK(cudns_io_wait(H[rk], nullptr)); if (rk == 0) saved.push_back(0); }
+        // ---- solverWrapper (cuda_main.cu:267-327)
+        std::vector<double> htime(nsteps), hpar1(nsteps), hpar2(nsteps);
+        team.barrier();
+        if (rk == 0) t0 = std::chrono::steady_clock::now();
+        for (int file = start + 1; file < nfiles + start + 1; file++) {
+            std::fill(hpar1.begin(), hpar1.end(), 0.0); std::fill(hpar2.begin(), hpar2.end(), 0.0);
+            CK(cudns_advance(H[rk], nsteps, htime.data(), hpar1.data(), hpar2.data()));
+            CK(cudns_write_fields_async(H[rk], outdir.c_str(), file));         // copyField(1) + writeField(file) without stalling the next file
+            if (!async_io) CK(cudns_io_wait(H[rk], nullptr));
+            write_prof(rk);
+            if (rk != 0) continue;
+            saved.push_back(file);
+            // par1 / par2 are refreshed every checkBulk steps: report the last refreshed entry like the reference's device arrays hold it
+            int last = ((nsteps - 1) / P.checkBulk) * P.checkBulk;
+            std::printf("file number: %d  \t step: %d  \t time: %lf  \t kin: %le  \t energy: %le\n", file, file * nsteps, htime[nsteps - 1], hpar1[last], hpar2[last]);
+            for (int t = 0; t < nsteps - 1; t += P.checkCFLcondition)
+                std::fprintf(sol, "%d %lf %lf %lf %lf\n", file * (t + 1), htime[t], hpar1[t], hpar2[t], htime[t + 1] - htime[t]);
+            std::fflush(sol);
+        }
+        uint64_t nw = 0;
+        CK(cudns_io_wait(H[rk], &nw));
+        team.add_written(nw);
+    });
+    std::fclose(sol);
+    nwritten = team.written;
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::vector<double>().swap(r); std::vector<double>().swap(u); std::vector<double>().swap(v); std::vector<double>().swap(w); std::vector<double>().swap(e);
     if (xdmf) {
-        double dtn = 0.0; CK(cudns_get_scalars(H, &dtn, nullptr, nullptr));
+        double dtn = 0.0; CK(cudns_get_scalars(H[0], &dtn, nullptr, nullptr));
         CK(cudns_write_xdmf((outdir + "/fields/fields.xmf").c_str(), 0, x.data(), P.mx, y.data(), P.my, z.data(), P.mz, saved.data(), (int)saved.size(),
                             dtn * nsteps, "ruvwe"));
     }
     const int stages = P.rk4 ? 4 : 3;
     std::printf("The total time is: %lf\nThe simulation time per time step is: %lf\n", secs, secs / ((double)nfiles * nsteps));
-    std::printf("cudns_run: %.1f Mpts*RK-stage/s (step loop + diagnostics + output hand-off), %llu field files written\n",
-                (double)N * stages * nfiles * nsteps / secs / 1e6, (unsigned long long)nwritten);
-    CK(cudns_destroy(H));
+    std::printf("cudns_run: %.1f Mpts*RK-stage/s on %d GPU%s (step loop + diagnostics + output hand-off), %llu field files written\n",
+                (double)N * stages * nfiles * nsteps / secs / 1e6, ngpus, ngpus > 1 ? "s" : "", (unsigned long long)nwritten);
+    for (int rk = 0; rk < ngpus; rk++) CK(cudns_destroy(H[rk]));
+    if (group) CK(cudns_team_destroy(group));
     std::printf("Simulation is finished! \n");
     return 0;
 }

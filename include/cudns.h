@@ -186,6 +186,14 @@ typedef void (*cudns_exchange_fn)(void *user, void *stream /* cudaStream_t */);
 /* transport (b): called once per RK stage (and once in set_state) on the solver's stream after the
  * send blocks are packed; must enqueue the exchange on that stream (or synchronise itself). */
 int cudns_set_exchange(cudns_handle h, cudns_exchange_fn fn, void *user);
+/* Several GPUs of one box from ONE process, without MPI or NCCL: n solvers created with nranks = n, rank = 0..n-1 on n devices, one
+ * host thread each (the role of the reference's MPI ranks, src/comm.cpp).  cudns_team_create maps the slabs' state blocks into each
+ * other (peer access: transport (a)) and installs host-side all-reduce / exchange callbacks that meet at a barrier; afterwards every
+ * collective call (cudns_set_state, cudns_advance, cudns_calc_*, cudns_stats_*, ...) must be made by all n threads in the same order.
+ * Destroy the team after the solvers. */
+typedef struct cudns_team *cudns_team_handle;
+int cudns_team_create(cudns_handle *solvers, int n, cudns_team_handle *out);
+int cudns_team_destroy(cudns_team_handle t);
 /* the CUDA stream the solver launches on (cudaStream_t), for event timing by the caller */
 int cudns_get_stream(cudns_handle h, void **stream);
 

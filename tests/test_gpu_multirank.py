@@ -223,6 +223,77 @@ def test_two_slabs_post_statistics():
     assert abs(extras[0]["Ret"] - float(tool["Ret"])) <= 1e-6
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("case", ["tgv_ls3", "tgv_rk4_f32"])
+def test_team_two_slabs_in_one_process(case):
+    """cudns_team_create: the library's own wiring of n solvers driven by n host threads of one process (peer mapping + host-side
+    all-reduce / exchange callbacks) -- no torch, no NCCL: equal to one slab"""
+    import ctypes as C
+
+    def p_of(nranks, rank):
+        p = cd.params_tgv(32, 4, mz=48, precision=int(case.endswith("f32")), lowStorage=int("ls3" in case), rk4=int("rk4" in case))
+        p.nranks = nranks; p.rank = rank; p.device = 0
+        return p
+    p1 = p_of(1, 0)
+    grid = cd.init_grid(p1)
+    full = cd.init_chit(p1, grid)
+    ref = cd.Solver(p1, grid); ref.set_state(full); ref.advance(8); single = ref.get_state(); b1 = ref.bulk()[0]; ref.close()
+    sols = [cd.Solver(p_of(2, r), grid) for r in range(2)]
+    arr = (C.c_void_p * 2)(*[s.h for s in sols])
+    team = C.c_void_p()
+    assert cd.lib().cudns_team_create(arr, 2, C.byref(team)) == 0, cd.lib().cudns_last_error()
+    out, bulk, errors = [None, None], [None, None], []
+
+    def worker(r):
+        try:
+            mzl = sols[r].mzl
+            sols[r].set_state([a[r * mzl:(r + 1) * mzl] for a in full])
+            sols[r].advance(8)
+            out[r] = sols[r].get_state(); bulk[r] = sols[r].bulk()[0]
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not any(t.is_alive() for t in th), "team run hung"
+    assert not errors, errors
+    for s in sols:
+        s.close()
+    cd.lib().cudns_team_destroy(team)
+    multi = [np.concatenate([out[r][f] for r in range(2)]) for f in range(5)]
+    errs = [relerr(a, b) for a, b in zip(conserved(multi), conserved(single))]
+    assert max(errs) < 1e-13, errs
+    assert bulk[0] == bulk[1] and abs(bulk[0] - b1) <= 1e-13 * b1
+
+
+@pytest.mark.timeout(300)
+def test_driver_two_slabs_reproduce_the_reference_channel_run(tmp_path):
+    """cudns_run ngpus=2 (two host threads, two slabs; samedevice=1 puts both on this box's GPU): the channel golden of the reference's
+    own GPU binary, fields written by both slabs into the same files"""
+    from common import CONFIGS, load_golden
+    name = "chan_s3v2"
+    cfg = CONFIGS[name]; g = load_golden(name)
+    out = tmp_path / "run"
+    os.makedirs(out / "fields")
+    for c, a in zip("ruvwe", g["file0"]):
+        np.ascontiguousarray(a).tofile(out / "fields" / ("%s.0000000.bin" % c))
+    keys = ("mx", "my", "mz", "stencilSize", "stencilVisc", "Lx", "Ly", "Lz", "CFL", "checkCFLcondition", "checkBulk", "Re", "Pr", "Ma",
+            "viscexp", "stretch", "forcing", "periodicX", "nonUniformX", "lowStorage")
+    exe = os.path.join(ROOT, "cudanavierstokes_b200", "cudns_run")
+    args = [exe, "case=channel", "restartFile=0", "nfiles=2", "nsteps=%d" % cfg["nsteps"], "outdir=%s" % out, "ngpus=2", "samedevice=1"]
+    args += ["%s=%r" % (k, cfg[k]) for k in keys]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = [np.fromfile(out / "fields" / ("%s.0000002.bin" % c)).reshape(g["file2"][0].shape) for c in "ruvwe"]
+    errs = [relerr(a, b) for a, b in zip(conserved(got), conserved(list(g["file2"])))]
+    assert max(errs) < 5e-12, errs
+    sol = np.loadtxt(out / "solution.txt")
+    assert np.allclose(sol[:, 1:], g["solution"][:, 1:], rtol=0, atol=2e-6)
+    assert "on 2 GPUs" in r.stdout
+
+
 @pytest.mark.timeout(600)
 def test_two_gpus_torchrun_peer_memory():
     import torch

@@ -7,7 +7,7 @@ CS = os.path.join(ROOT, "cudanavierstokes_b200", "csrc")
 # every prototype of the header that takes (or creates) a solver handle
 hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "cudns.h")).read(), flags=re.S)
 protos = [(m.group(1), " ".join(m.group(2).split())) for m in re.finditer(r"\bint\s+cudns_(\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
-          if "cudns_handle" in m.group(2)]
+          if "cudns_handle" in m.group(2) and not m.group(1).startswith("team_")]      # (cudns_team_* works on top of the public symbols)
 out = open(os.path.join(CS, "abi_dispatch.cpp")).read().split('extern "C" {')[0] + 'extern "C" {\n'
 for n, params in protos:
     args = [re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[[^\]]*\])?$", a.strip())[0] for a in params.split(",")]
