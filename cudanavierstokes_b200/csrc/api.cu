@@ -205,7 +205,6 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         S->fast_ty = (fe && std::string(fe) == "16") ? 16 : 8;
         S->fast = p->viscexp == 1.0 && p->periodicX && !p->nonUniformX && !p->boundaryLayer && !(we && (std::string(we) == "0" || std::string(we) == "1")) &&
                   (size_t)fast_smem_bytes(s, S->fast_ty) <= prop.sharedMemPerBlockOptin;
-        S->nfb = S->fast ? FAST_NFB : 5;
         // fifth generation: two x-adjacent points per thread, every Runge-Kutta stage shape; needs an even mx (16-byte rows)
         // It serves Kutta RK3 and RK4 by default (the fourth generation cannot: those stages fell back to the lean kernel); for
         // low-storage RK3 the fourth generation is still ~5 % faster (2 x 8 warps per SM hide more latency than 8 warps with two
@@ -214,11 +213,11 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         const bool ls3 = p->lowStorage && !p->rk4;
         const bool want = kF32 || (de ? std::string(de) != "0" : !ls3);
         S->duo = S->fast && (!fe || kF32) && mx % 2 == 0 && want && (size_t)duo_smem_bytes(s) <= prop.sharedMemPerBlockOptin;
-        if (kF32 && !S->duo) {
-            // `myprec float` (globals.h:5-6) is built for the set-ups the fifth-generation kernel serves
-            set_error("precision = 1 (float) needs periodicX = 1, nonUniformX = 0, boundaryLayer = 0, viscexp = 1 and an even mx");
-            cudns_destroy(S); return CUDNS_EUNSUPPORTED;
-        }
+        // `myprec float` (globals.h:5-6): the fifth generation where it applies, the lean kernel for everything else (walls,
+        // stretched x, boundary layer, non-linear viscosity, odd mx); there is no single-precision fourth generation
+        if (kF32 && !S->duo) S->fast = false;
+        if (kF32 && !S->duo && mx % 4) { set_error("precision = 1 (float) outside the periodic / uniform / linear-viscosity set-ups needs mx % 4 == 0 (16-byte rows)"); cudns_destroy(S); return CUDNS_EINVAL; }
+        S->nfb = S->fast ? FAST_NFB : 5;
     }
     S->block_doubles = (size_t)S->nstate * S->nfb * L.vol;
     S->block_doubles = (S->block_doubles + 31) / 32 * 32;                       // keep the mailbox 256-byte aligned
@@ -308,17 +307,18 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     sc0[SC_DPDZ] = p->forcing ? 0.00372 : 0.0;                 // cuda_utils.cu:68-70
     CKC(cudaMemcpy(S->d_scal, sc0, sizeof(sc0), cudaMemcpyHostToDevice));
     // opt in to the large dynamic shared memory the stage kernel needs; fail loudly if the device cannot give it
-    if (!kF32 && (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
+    const bool lean_maps = !(kF32 && S->duo);        // single precision: a solver is served by one kernel generation
+    if (lean_maps && (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
         const int CXb = 32 + 2 * GX;
-        const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lty + 2 * s;
-        for (int b = 0; !kF32 && b < S->nstate; b++) {
+        const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lean_box_rows(lty, s);
+        for (int b = 0; lean_maps && b < S->nstate; b++) {
             if ((rc = make_map(&S->lmaps[b].qbox, L, S->state[b], 5, CXb, LYb)) || (rc = make_map(&S->lmaps[b].qint, L, S->state[b], 5, 32, lty)) ||
                 (rc = make_map(&S->lmaps[b].thbox, L, S->theta, 1, CXb, LYb)) || (rc = make_map(&S->lmaps[b].thint, L, S->theta, 1, 32, lty))) {
                 cudns_destroy(S); return rc;
             }
         }
-        if (!kF32 && ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty))))) { cudns_destroy(S); return rc; }
+        if (lean_maps && ((rc = make_rmap(&S->rmap[0], L, S->R1, lty)) || (S->R2 && (rc = make_rmap(&S->rmap[1], L, S->R2, lty))))) { cudns_destroy(S); return rc; }
         const char *we = getenv("CUDNS_WIDE");
         S->wide = !kF32 && lean_wide_ok(kc) && !(we && std::string(we) == "0") && (size_t)lean_smem_wide_bytes(s) <= prop.sharedMemPerBlockOptin;
         if (S->fast && !kF32) {
@@ -357,7 +357,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
             }
         }
         if (S->wide) {
-            const int wty = CUDNS_LEAN_TY_WIDE, WYb = wty + 2 * s;
+            const int wty = CUDNS_LEAN_TY_WIDE, WYb = lean_box_rows(wty, s);
             for (int b = 0; b < S->nstate; b++) {
                 if ((rc = make_map(&S->wmaps[b].qbox, L, S->state[b], 5, CXb, WYb)) || (rc = make_map(&S->wmaps[b].qint, L, S->state[b], 5, 32, wty)) ||
                     (rc = make_map(&S->wmaps[b].thbox, L, S->theta, 1, CXb, WYb)) || (rc = make_map(&S->wmaps[b].thint, L, S->theta, 1, 32, wty))) {

@@ -146,6 +146,8 @@ constexpr int DUO_TX = 64, DUO_TY = 8;
 // rows of its halo'd plane: 8 + 2s, rounded up until one field of the box is a multiple of 128 bytes (TMA destinations; single
 // precision with s = 1, 3 only)
 constexpr int duo_box_rows(int s) { int cy = DUO_TY + 2 * s; while (((DUO_TX + 2 * GX) * cy * (int)sizeof(real)) % 128) cy++; return cy; }
+// rows of the lean kernels' halo'd plane (40 cells wide): ty + 2s, rounded up the same way
+constexpr int lean_box_rows(int ty, int s) { int cy = ty + 2 * s; while ((40 * cy * (int)sizeof(real)) % 128) cy++; return cy; }
 struct DuoMaps {
     CUtensorMap q4box, a3box;               // halo'd tile (72 x (8+2s)) of (rho,u,v,w) and of (H,T,theta)
     CUtensorMap q4int, a3int;               // tile interior (64 x 8) of the same (plane S ahead, for the z ring)

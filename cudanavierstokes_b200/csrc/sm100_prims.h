@@ -13,7 +13,22 @@ __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
 }
+#ifndef MBAR_SUSPEND_NS
+#define MBAR_SUSPEND_NS 0     // > 0: try_wait may park the warp in hardware for up to that many ns before it reports "not yet"
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+#if MBAR_SUSPEND_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(a), "r"(parity), "r"((uint32_t)MBAR_SUSPEND_NS) : "memory");
+    return;
+#endif
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"

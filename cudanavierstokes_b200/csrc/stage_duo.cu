@@ -36,12 +36,8 @@ __global__ void __launch_bounds__(256) derive_aux_kernel(const __grid_constant__
 void launch_derive_aux(const KConst &kc, real *q8, cudaStream_t st) { derive_aux_kernel<<<148 * 8, 256, 0, st>>>(kc, q8); }
 
 #ifdef CUDNS_F32
-// the older kernel generations exist in double precision only (api.cu never selects them in this build)
-void launch_rhs_stage_lean(const KConst &, const StagePtrs &, const StageCoef &, const LeanMaps &, bool, cudaStream_t) {}
+// the fourth generation exists in double precision only (api.cu never selects it in this build)
 void launch_rhs_stage_fast(const KConst &, const StagePtrs &, const StageCoef &, const FastMaps &, int, cudaStream_t) {}
-bool lean_wide_ok(const KConst &) { return false; }
-int lean_smem_wide_bytes(int) { return 0; }
-int lean_smem_bytes(int, bool) { return 0; }
 int fast_smem_bytes(int, int) { return 0; }
 void launch_theta_march(const KConst &, const real *, real *, cudaStream_t);
 #endif

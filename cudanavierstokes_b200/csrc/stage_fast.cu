@@ -30,6 +30,9 @@
 #ifndef FAST_L2_HINTS
 #define FAST_L2_HINTS 0       // 1: L2 eviction hints on the TMA loads + streaming stores (measured: no gain, 143 vs 149 B/pt read)
 #endif
+#ifndef FAST_LAST_ISSUES
+#define FAST_LAST_ISSUES 0    // 1: the last warp to empty the ring tile sends the next plane bundle (instead of thread 0 after its z sums)
+#endif
 #ifndef FAST_ONESIDED
 #define FAST_ONESIDED 0       // 1: one neighbour at a time (fewer registers, one more FP64 instruction per neighbour pair)
 #endif
@@ -163,6 +166,9 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     uint64_t *mbar_p = (uint64_t *)(smem + G::DATA_D);
     uint32_t *tmem_holder = (uint32_t *)(mbar_p + 4);
     double *dt_s = (double *)(mbar_p + 5);              // dt, read once per CTA
+#if FAST_LAST_ISSUES
+    unsigned int *arrivals = (unsigned int *)(mbar_p + 6);   // warps that have emptied the ring tile, counted over the chunk
+#endif
 
     const Layout &L = c.L;
     const int tid = threadIdx.x;
@@ -178,6 +184,9 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     if (tid == 0) {
         mbar_init(mb_full0, 1); mbar_init(mb_full0 + 8, 1); mbar_init(mb_free, TY);
         *dt_s = *c.dt;
+#if FAST_LAST_ISSUES
+        *arrivals = 0u;
+#endif
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -257,8 +266,21 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
             const double *src = intb + ty * TX + tx;
             const double r0 = src[0], r1 = src[NT], r2 = src[2 * NT], r3 = src[3 * NT], r4 = src[4 * NT], r5 = src[5 * NT], r6 = src[6 * NT];
             __syncwarp();
+#if FAST_LAST_ISSUES
+            tmem_st7d_nowait(zs[2 * S], r0, r1, r2, r3, r4, r5, r6);
+            // the warp that arrives last knows every warp is done with intb and with plane k-1: it sends the loads of plane k+1
+            // right away, a whole plane ahead (the wait completes at once; it is there for the acquire)
+            if (tx == 0) {
+                mbar_arrive(mb_free);
+                if (atomicAdd(arrivals, 1u) == (unsigned)((kk + 1) * TY - 1) && k + 1 < kend_now()) {
+                    mbar_wait(mb_free, (uint32_t)kk & 1u);
+                    issue_bundle(k + 1, b ^ 1);
+                }
+            }
+#else
             if (tx == 0) mbar_arrive(mb_free);                    // intb is consumed as soon as the values sit in registers
             tmem_st7d_nowait(zs[2 * S], r0, r1, r2, r3, r4, r5, r6);
+#endif
         }
         double C[NF];
         slot_wait(sl, C);
@@ -292,10 +314,12 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         }
         // ---- the elected thread: once every warp has emptied intb (which also means it is done with plane k-1 and its buffer),
         // the loads of plane k+1 go out; they have the x / y directions, the assembly and the update of this plane to land
+#if !FAST_LAST_ISSUES
         if (tn == 0 && k + 1 < kend_now()) {
             mbar_wait(mb_free, (uint32_t)kk & 1u);
             issue_bundle(k + 1, b ^ 1);
         }
+#endif
 
         // ---- x and y directions: neighbours straight from the TMA-landed plane, [7][CY][CX]
         {

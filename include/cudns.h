@@ -68,7 +68,8 @@ typedef struct cudns_params {
     int precision;             /* `myprec` (globals.h:5-6) as a run-time value: 0 = double (default), 1 = float.  Device state, coefficient
                                 * tables and all kernel arithmetic run in that precision; host arrays crossing this ABI are double in both
                                 * (copyField casts, cuda_utils.cu:317-355), reduced scalars and statistics are accumulated in double.
-                                * float is built for the periodic / uniform / linear-viscosity set-ups with an even mx (Taylor-Green) */
+                                * float serves every set-up double does (walls, stretched x, boundary layer, any viscosity law); outside
+                                * the periodic / uniform / linear-viscosity case it needs mx % 4 == 0 (16-byte rows) */
     int reserved[3];
 } cudns_params;
 

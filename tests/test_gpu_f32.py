@@ -76,9 +76,75 @@ def test_f32_history_and_diagnostics():
     s.close()
 
 
-def test_f32_refuses_what_it_is_not_built_for():
-    op = ob.params_channel()
+@pytest.mark.parametrize("name", ["chan_s3v2", "chan_s2v2", "bl_s3v2"])
+def test_f32_walls_stretched_grid_and_boundary_layer_vs_reference_gpu_binary(name):
+    """the set-ups the lean kernel serves (isothermal walls / boundary layer with sponge and blowing-suction, tanh-stretched x,
+    T^0.75 and T^1.5 viscosity) in single precision, from the reference's own file 0 to its file 2 (FP64 goldens)"""
+    from common import CONFIGS, apply_cfg, blasius_profiles, conserved, load_golden
+    cfg = CONFIGS[name]; g = load_golden(name)
+    op = apply_cfg(ob.params_tgv(24, 3), cfg)
+    cp = apply_cfg(cd.Params(), cfg); cp.gam = 1.4; cp.TwallTop = cp.TwallBot = 1.0; cp.quirk_q1 = 1; cp.nranks = 1; cp.precision = 1
+    for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
+              "kC", "LP", "amp1", "amp2", "omega2"):
+        setattr(cp, k, getattr(op, k))
+    grid = cd.init_grid(cp)
+    s = cd.Solver(cp, grid)
+    if cfg["case"] == "blayer":
+        x, r, u, w, e = blasius_profiles()
+        sx, sz, ref, ic = cd.build_sponge(cp, grid, x[1:], r[1:], u[1:], w[1:])
+        s.set_sponge(sx, sz, ref)
+    s.set_state(list(g["file0"]))
+    s.advance(cfg["nsteps"]); s.advance(cfg["nsteps"])
+    got = conserved(s.get_state()); ref = conserved(list(g["file2"]))
+    mom = max(np.abs(ref[k]).max() for k in (1, 2, 3))
+    errs = [relerr(got[0], ref[0])] + [relerr(got[k], ref[k], floor=mom) for k in (1, 2, 3)] + [relerr(got[4], ref[4])]
+    print("f32", name, ["%.1e" % e for e in errs])
+    assert errs[0] < 2e-5 and errs[4] < 2e-5 and max(errs[1:4]) < 2e-5, errs       # measured: 4e-6, 4e-6, 5e-6
+    sc = s.scalars()
+    assert abs(sc["dt"] - g["dt_dpdz"][-1, 0]) <= 1e-4 * sc["dt"]
+    if cfg["forcing"]:
+        assert abs(sc["dpdz"] - g["dt_dpdz"][-1, 1]) <= 1e-3 * abs(sc["dpdz"])
+    s.close()
+
+
+@pytest.mark.parametrize("case", ["channel_linear_s4v4", "channel_linear_s1v1", "periodic_sqrt_visc_s3v3", "periodic_odd_tiles_s4v2"])
+def test_f32_lean_kernel_variants_vs_fp64_oracle(case):
+    """the remaining variants of the lean kernel in single precision: 8 staged quantities with walls (linear viscosity law), 9
+    without walls (periodic box, mu ~ sqrt(T)), and a periodic box the fifth generation does not take (mx = 2 mod 4 is refused,
+    mx = 36: ragged tiles)"""
+    if case.startswith("channel"):
+        s_, v_ = (4, 4) if case.endswith("s4v4") else (1, 1)
+        op = apply_cfg_channel(s_, v_)
+        o, s, grid = make_pair32(op)
+        o.init_channel(); st = o.state()
+    elif case.startswith("periodic_sqrt"):
+        op = ob.params_tgv(24, 3, mx=32, my=20, mz=24, viscexp=0.5, Ma=0.5)
+        o, s, grid = make_pair32(op)
+        st = smooth_random_state(o)
+    else:
+        op = ob.params_tgv(24, 4, stencilVisc=2, mx=36, my=20, mz=24, viscexp=0.75, Ma=0.5)
+        o, s, grid = make_pair32(op)
+        st = smooth_random_state(o)
+    o.set_state(st); s.set_state(st)
+    a = s.rhs(); b = o.rhs()
+    rerr = [relerr(x, y, floor=max(np.abs(z).max() for z in b[1:4]) if 1 <= k <= 3 else 0.0) for k, (x, y) in enumerate(zip(a, b))]
+    o.run(5); s.advance(5)
+    errs = cons_errs(s.get_state(), o.state())
+    print("f32 lean", case, "rhs", ["%.1e" % e for e in rerr], "5 steps", ["%.1e" % e for e in errs])
+    assert max(rerr) < 2e-5, rerr                                                    # measured: 4e-6
+    assert errs[0] < 5e-6 and errs[4] < 5e-6 and max(errs[1:4]) < 1e-5, errs        # measured: 6e-7, 4e-7, 2e-6
+    s.close()
+
+
+def apply_cfg_channel(s_, v_):
+    from common import CONFIGS, apply_cfg
+    op = apply_cfg(ob.params_tgv(24, 3), dict(CONFIGS["chan_s3v2"], stencilSize=s_, stencilVisc=v_, viscexp=1.0, mx=64, my=24, mz=32))
+    return op
+
+
+def test_f32_refuses_a_row_length_it_cannot_stage():
+    """single precision outside the fifth generation's set-ups needs 16-byte rows: mx % 4 == 0"""
+    op = ob.params_tgv(24, 3, mx=38, my=20, mz=24, viscexp=0.5)
     cp = copy_params(op, cd.Params()); cp.nranks = 1; cp.precision = 1
-    cp.mx, cp.my, cp.mz = 32, 24, 24
     with pytest.raises(cd.CudnsError):
         cd.Solver(cp)

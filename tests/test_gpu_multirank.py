@@ -119,7 +119,7 @@ def test_two_slabs_equal_one(case, peer):
     assert max(errs) < 1e-13, errs          # multi-GPU == single-GPU to 1e-13 (observed: identical)
 
 
-def _golden_params(name):
+def _golden_params(name, prec=0):
     import oracle_binding as ob
     from common import CONFIGS, apply_cfg
     cfg = CONFIGS[name]
@@ -130,17 +130,17 @@ def _golden_params(name):
         for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
                   "kC", "LP", "amp1", "amp2", "omega2"):
             setattr(cp, k, getattr(op, k))
-        cp.nranks = nranks; cp.rank = rank; cp.device = 0
+        cp.nranks = nranks; cp.rank = rank; cp.device = 0; cp.precision = prec
         return cp
     return cfg, p_of
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("peer", [True, False])
-def test_two_slabs_channel_forcing(peer):
+@pytest.mark.parametrize("peer,prec", [(True, 0), (False, 0), (True, 1)])
+def test_two_slabs_channel_forcing(peer, prec):
     """isothermal-wall channel with the pressure-gradient controller: the bulk integrals (calcPressureGrad calc_stress.cu:98-120) are
     cross-rank SUMs, dt a cross-rank MAX; walls in x, stretched grid, periodic z across the slab seam"""
-    cfg, p_of = _golden_params("chan_s3v2")
+    cfg, p_of = _golden_params("chan_s3v2", prec)
     p1 = p_of(1, 0)
     grid = cd.init_grid(p1)
     full = cd.init_channel(p1, grid)
@@ -150,18 +150,20 @@ def test_two_slabs_channel_forcing(peer):
     errs = [relerr(a, b) for a, b in zip(conserved(multi), conserved(single))]
     # the forcing integrals are summed per slab and then across ranks: a different order than one device's single sum, so dpdz (and
     # with it the state) agrees to round-off, not bit for bit
-    assert max(errs) < 1e-12, errs
-    assert abs(sc2[0]["dpdz"] - sc1["dpdz"]) <= 1e-12 * abs(sc1["dpdz"])
-    assert abs(sc2[0]["dt"] - sc1["dt"]) <= 1e-14 * sc1["dt"]
+    # (single precision: dpdz still agrees to double round-off -- the integrals are double sums --, but one flipped float rounding
+    # of dt * dpdz is a 6e-8 difference in the state)
+    assert max(errs) < (1e-12 if prec == 0 else 2e-6), errs
+    assert abs(sc2[0]["dpdz"] - sc1["dpdz"]) <= (1e-12 if prec == 0 else 1e-6) * abs(sc1["dpdz"])
+    assert abs(sc2[0]["dt"] - sc1["dt"]) <= (1e-14 if prec == 0 else 1e-6) * sc1["dt"]
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("peer", [True, False])
-def test_two_slabs_boundary_layer(peer):
+@pytest.mark.parametrize("peer,prec", [(True, 0), (False, 0), (True, 1)])
+def test_two_slabs_boundary_layer(peer, prec):
     """spatially developing boundary layer: z is NOT periodic (the global bottom / top slabs have no neighbour there and rebuild the
     extrapolation ghosts on chip, api.cu ghost_targets / handshake), sponges and wall blowing/suction indexed by the GLOBAL plane"""
     from common import blasius_profiles
-    cfg, p_of = _golden_params("bl_s3v2")
+    cfg, p_of = _golden_params("bl_s3v2", prec)
     p1 = p_of(1, 0)
     grid = cd.init_grid(p1)
     x, r, u, w, e = blasius_profiles()

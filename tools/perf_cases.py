@@ -1,6 +1,6 @@
 """Throughput of the non-periodic BASELINE configurations at their full sizes (the lean GEN stage kernel):
 C3 supersonic isothermal channel 160x192x192 (4th order: s=v=2, and the preset's s=3,v=2), C4 boundary layer 240x64x2048
-with sponges and wall blowing/suction (s=3,v=2).  usage: tools/perf_cases.py [steps]"""
+with sponges and wall blowing/suction (s=3,v=2).  usage: tools/perf_cases.py [steps] [f32]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,9 +9,10 @@ import cudanavierstokes_b200 as cd
 from ref_cases import CONFIGS, apply_cfg, blasius_profiles
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+prec = int(len(sys.argv) > 2 and sys.argv[2] == "f32")
 
 def run(name, cfg, over):
-    p = apply_cfg(cd.Params(), dict(cfg, **over)); p.gam = 1.4; p.TwallTop = p.TwallBot = 1.0; p.quirk_q1 = 1; p.nranks = 1
+    p = apply_cfg(cd.Params(), dict(cfg, **over)); p.gam = 1.4; p.TwallTop = p.TwallBot = 1.0; p.quirk_q1 = 1; p.nranks = 1; p.precision = prec
     ref = cd.params_blayer() if cfg["case"] == "blayer" else cd.params_channel()
     for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
               "kC", "LP", "amp1", "amp2", "omega2"):
@@ -30,8 +31,8 @@ def run(name, cfg, over):
     st = s.get_state()
     N = p.mx * p.my * p.mz
     ok = all(np.isfinite(a).all() for a in st)
-    print("perf_case %-28s %4dx%4dx%4d s=%d v=%d: %.3f ms/step -> %.2f Gpts*stage/s | theta %.3f ms stage %.3f ms | finite=%s" %
-          (name, p.mx, p.my, p.mz, p.stencilSize, p.stencilVisc, dt / steps * 1e3, 3 * N * steps / dt / 1e9,
+    print("perf_case%s %-28s %4dx%4dx%4d s=%d v=%d: %.3f ms/step -> %.2f Gpts*stage/s | theta %.3f ms stage %.3f ms | finite=%s" %
+          (" f32" if prec else "", name, p.mx, p.my, p.mz, p.stencilSize, p.stencilVisc, dt / steps * 1e3, 3 * N * steps / dt / 1e9,
            prof["theta_ms"], prof["rhs_stage_ms"], ok), flush=True)
     s.close()
 
