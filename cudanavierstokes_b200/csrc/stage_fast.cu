@@ -33,6 +33,10 @@
 #ifndef FAST_LAST_ISSUES
 #define FAST_LAST_ISSUES 0    // 1: the last warp to empty the ring tile sends the next plane bundle (instead of thread 0 after its z sums)
 #endif
+#ifndef FAST_SPLIT_BAR
+#define FAST_SPLIT_BAR 0      // 1: the ring tile (needed at the top of a plane) completes on a barrier of its own and is loaded first;
+                              //    the halo'd plane (needed after the z sums) is waited for later
+#endif
 #ifndef FAST_ONESIDED
 #define FAST_ONESIDED 0       // 1: one neighbour at a time (fewer registers, one more FP64 instruction per neighbour pair)
 #endif
@@ -180,9 +184,15 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
 
     // mb_full[b]: the TMA loads of a plane bundle into buffer b have landed; mb_free: every warp has taken its ring values out of intb
     const uint32_t mb_full0 = smem_u32(mbar_p), mb_free = mb_full0 + 16;
+#if FAST_SPLIT_BAR
+    const uint32_t mb_int = mb_full0 + 24;
+#endif
     if (ty == 0) tmem_alloc(smem_u32(tmem_holder), G::NCOLS);
     if (tid == 0) {
         mbar_init(mb_full0, 1); mbar_init(mb_full0 + 8, 1); mbar_init(mb_free, TY);
+#if FAST_SPLIT_BAR
+        mbar_init(mb_int, 1);
+#endif
         *dt_s = *c.dt;
 #if FAST_LAST_ISSUES
         *arrivals = 0u;
@@ -202,8 +212,17 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
     auto issue_bundle = [&](int k, int b) {
         const uint32_t mb = mb_full0 + 8 * b;
         const uint32_t s_box = s_base + (uint32_t)(b * G::BUF_D * 8), s_e = s_box + (uint32_t)(G::BOX_D * 8), s_op = s_e + (uint32_t)(G::E_D * 8);
+#if FAST_SPLIT_BAR
+        mbar_expect_tx(mb_int, (uint32_t)(G::INT_D * sizeof(double)));
+        tma_load_4d(s_int, &tm.q4int, mb_int, i0 + GX, j0 + L.gy, k + S + L.gz, 0);
+        tma_load_4d(s_int + 4 * NT * 8, &tm.a3int, mb_int, i0 + GX, j0 + L.gy, k + S + L.gz, 0);
+        mbar_expect_tx(mb, (uint32_t)((G::BOX_D + G::E_D + (useA ? G::OP_D : 0)) * sizeof(double)));
+        tma_load_4d(s_box, &tm.q4box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
+        tma_load_4d(s_box + 4 * CSZ * 8, &tm.a3box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
+        tma_load_3d(s_e, &tm.eint, mb, i0 + GX, j0 + L.gy, k + L.gz);
+        if (useA) tma_load_4d(s_op, &tm.opa, mb, i0, j0, k, 0);
+#elif FAST_L2_HINTS
         mbar_expect_tx(mb, (uint32_t)((G::BOX_D + G::E_D + (useA ? G::OP_D : 0) + G::INT_D) * sizeof(double)));
-#if FAST_L2_HINTS
         tma_load_4d_hint(s_box, &tm.q4box, mb, i0, j0 + L.gy - S, k + L.gz, 0, L2_EVICT_FIRST);
         tma_load_4d_hint(s_box + 4 * CSZ * 8, &tm.a3box, mb, i0, j0 + L.gy - S, k + L.gz, 0, L2_EVICT_FIRST);
         tma_load_4d_hint(s_int, &tm.q4int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0, L2_EVICT_LAST);
@@ -211,6 +230,7 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         tma_load_3d_hint(s_e, &tm.eint, mb, i0 + GX, j0 + L.gy, k + L.gz, L2_EVICT_FIRST);
         if (useA) tma_load_4d_hint(s_op, &tm.opa, mb, i0, j0, k, 0, L2_EVICT_FIRST);
 #else
+        mbar_expect_tx(mb, (uint32_t)((G::BOX_D + G::E_D + (useA ? G::OP_D : 0) + G::INT_D) * sizeof(double)));
         tma_load_4d(s_box, &tm.q4box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
         tma_load_4d(s_box + 4 * CSZ * 8, &tm.a3box, mb, i0, j0 + L.gy - S, k + L.gz, 0);
         tma_load_4d(s_int, &tm.q4int, mb, i0 + GX, j0 + L.gy, k + S + L.gz, 0);
@@ -258,7 +278,11 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
         for (int n = 0; n < R; n++) zs[n] = tbase + ring_off[S - 1][s0 + n];
         const int own = (ty + S) * CX + (tx + GX);
         // the first buffer's barrier has already completed two phases in the prologue: the parities line up (phase 2 -> parity 0)
+#if FAST_SPLIT_BAR
+        mbar_wait(mb_int, (uint32_t)kk & 1u);
+#else
         mbar_wait(mb_full0 + 8 * b, (uint32_t)(kk >> 1) & 1u);
+#endif
         // ---- own point of plane k out of the ring; plane k+S into the ring (no arithmetic: the state carries H and T)
         Slot sl;
         slot_issue(zs[S], sl);
@@ -322,6 +346,9 @@ stage_kernel(const __grid_constant__ KConst c, const __grid_constant__ StagePtrs
 #endif
 
         // ---- x and y directions: neighbours straight from the TMA-landed plane, [7][CY][CX]
+#if FAST_SPLIT_BAR
+        mbar_wait(mb_full0 + 8 * b, (uint32_t)(kk >> 1) & 1u);
+#endif
         {
             const double *pc = box + own;
 #pragma unroll

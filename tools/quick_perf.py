@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import cudanavierstokes_b200 as cd
 
-def run(n, s, v, scheme="ls3", reps=5, prec=0):
+def run(n, s, v, scheme="ls3", reps=int(os.environ.get("QP_REPS", "5")), prec=0):
     p = cd.params_tgv(n, s, stencilVisc=v, lowStorage=int(scheme == "ls3"), rk4=int(scheme == "rk4")); p.nranks = 1; p.precision = prec
     g = cd.init_grid(p)
     sol = cd.Solver(p, g)
