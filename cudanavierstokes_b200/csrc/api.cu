@@ -311,7 +311,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
     if (lean_maps && (size_t)lean_smem_bytes(s, kc.viscmode == 1) > prop.sharedMemPerBlockOptin) { set_error("device shared memory too small for the stage kernel"); cudns_destroy(S); return CUDNS_EUNSUPPORTED; }
     {   // TMA descriptors: halo'd tile and tile interior of every state buffer and of theta
         const int CXb = 32 + 2 * GX;
-        const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : CUDNS_LEAN_TY_GENERAL, LYb = lean_box_rows(lty, s);
+        const int lty = kc.viscmode == 1 ? CUDNS_LEAN_TY_LINEAR : lean_ty_general(s), LYb = lean_box_rows(lty, s);
         for (int b = 0; lean_maps && b < S->nstate; b++) {
             if ((rc = make_map(&S->lmaps[b].qbox, L, S->state[b], 5, CXb, LYb)) || (rc = make_map(&S->lmaps[b].qint, L, S->state[b], 5, 32, lty)) ||
                 (rc = make_map(&S->lmaps[b].thbox, L, S->theta, 1, CXb, LYb)) || (rc = make_map(&S->lmaps[b].thint, L, S->theta, 1, 32, lty))) {

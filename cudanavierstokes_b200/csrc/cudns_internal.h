@@ -122,7 +122,11 @@ struct StageMaps {
 #ifndef CUDNS_LEAN_TY_LINEAR
 #define CUDNS_LEAN_TY_LINEAR 12
 #endif
-#define CUDNS_LEAN_TY_GENERAL 8
+#ifndef CUDNS_LEAN_TY_GENERAL_LOW
+#define CUDNS_LEAN_TY_GENERAL_LOW 12
+#endif
+// 9 quantities: 8 rows where the rings of 12 would not fit tensor memory (s = 4) or the register cap of two resident CTAs (float)
+constexpr int lean_ty_general(int s) { return (sizeof(real) == 8 && s <= 3) ? CUDNS_LEAN_TY_GENERAL_LOW : 8; }
 struct LeanMaps {
     CUtensorMap qbox, qint, thbox, thint;   // input state / theta: halo'd tile and tile interior
     CUtensorMap qbint;                      // base state, tile interior (Kutta RK3 / RK4)

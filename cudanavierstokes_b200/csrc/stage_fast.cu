@@ -23,7 +23,7 @@
 // written by this kernel (cudns_set_state, the lean kernels).
 // Reference: cuda_rhs.cu:9-396, calc_stress.cu:20-96, cuda_main.cu:126-216,218-247 (see stage_lean.inc for the algebra).
 #define LEAN_TY8 CUDNS_LEAN_TY_LINEAR
-#define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
+#define LEAN_TY9 8
 #include "stage_lean.inc"
 #include "stage_point.h"
 

@@ -1,6 +1,6 @@
 // stage kernel instantiations for stencilSize = 3 (see stage_lean.inc)
 #define LEAN_TY8 CUDNS_LEAN_TY_LINEAR
-#define LEAN_TY9 CUDNS_LEAN_TY_GENERAL
+#define LEAN_TY9 lean_ty_general(3)
 #include "stage_lean.inc"
 namespace cudns {
 void launch_lean_s3(const KConst &kc, const StagePtrs &p, const StageCoef &c, const LeanMaps &maps, bool gen, bool wide, cudaStream_t st) {
@@ -14,6 +14,6 @@ void launch_lean_s3(const KConst &kc, const StagePtrs &p, const StageCoef &c, co
 }
 int lean_smem_wide_s3() { return (int)lean::Cfg<3, 16, 8>::bytes; }
 int lean_smem_s3(bool linear_visc) {
-    return (int)(linear_visc ? lean::Cfg<3, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<3, CUDNS_LEAN_TY_GENERAL, 9>::bytes);
+    return (int)(linear_visc ? lean::Cfg<3, CUDNS_LEAN_TY_LINEAR, 8>::bytes : lean::Cfg<3, lean_ty_general(3), 9>::bytes);
 }
 }  // namespace cudns
