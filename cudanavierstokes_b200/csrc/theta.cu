@@ -57,9 +57,9 @@ __device__ __forceinline__ real dwdz_edge(const KConst &c, const real *__restric
 #pragma unroll
     for (int l = 1; l <= V; l++) {
         real wp, wm;
-        if (k + l >= kglob_hi) wp = 2.0 * W[L.idx(ic, jc, kglob_hi - 1)] - W[L.idx(ic, jc, 2 * (kglob_hi - 1) - (k + l))];
+        if (k + l >= kglob_hi) wp = RC(2.0) * W[L.idx(ic, jc, kglob_hi - 1)] - W[L.idx(ic, jc, 2 * (kglob_hi - 1) - (k + l))];
         else wp = W[g0 + (size_t)l * L.plane];
-        if (k - l < kglob_lo) wm = 2.0 * W[L.idx(ic, jc, kglob_lo)] - W[L.idx(ic, jc, 2 * kglob_lo - (k - l))];
+        if (k - l < kglob_lo) wm = RC(2.0) * W[L.idx(ic, jc, kglob_lo)] - W[L.idx(ic, jc, 2 * kglob_lo - (k - l))];
         else wm = W[g0 - (size_t)l * L.plane];
         dwdz = fma(c.c1[2][l], wp - wm, dwdz);
     }
@@ -103,7 +103,7 @@ theta_march_kernel(const __grid_constant__ KConst c, const real *__restrict__ q,
     const real *puh = q + L.vol + L.idx(min(max(hgi, -GX), L.mx + GX - 1), jc, kfirst);
     const real *pvh = q + 2 * L.vol + L.idx(ic, j0 + hyr - V, kfirst);
     real *pt = theta + g00;
-    const real xpi = (GEN && c.nonUniformX) ? c.xp[ic] : 1.0;
+    const real xpi = (GEN && c.nonUniformX) ? c.xp[ic] : RC(1.0);
     // shared-memory slots (doubles, buffer 0)
     const int o_u = ty * UX + GX + tx, o_uh = ty * UX + hxc, o_v = (V + ty) * TXT + tx, o_vh = hyr * TXT + tx;
     // image flags: 1 x-low, 2 x-high, 4 y-low, 8 y-high (perBCx / perBCy, boundary.h:38-46)
@@ -151,7 +151,7 @@ theta_march_kernel(const __grid_constant__ KConst c, const real *__restrict__ q,
                         if (bl && c.perturbed && perturb_theta(c, j, k + c.kstart, pv2)) val = pv2;
                     } else {
                         const int gq = tx - V + 1, last = GX + nxt - 1;
-                        val = bl ? 2.0 * row[last] - row[last - gq] : -row[last - gq + 1];
+                        val = bl ? RC(2.0) * row[last] - row[last - gq] : -row[last - gq + 1];
                     }
                     su[boff_u + o_uh] = val;
                 }
@@ -355,9 +355,12 @@ void launch_theta_tma(const KConst &kc, const real *q, real *theta, const ThetaM
 void launch_theta_march(const KConst &kc, const real *q, real *theta, cudaStream_t st) {
     const int gx = (kc.L.mx + TXT - 1) / TXT, gy = (kc.L.my + TYT - 1) / TYT;
     const int nk = kc.L.mz + 2 * kc.v;
-    // z chunks: every chunk pays a 2V-plane prologue of w; aim at a few waves of 148 SMs x 3 CTAs
-    int nzc = 1;
-    while (gx * gy * nzc < 148 * 3 * 4 && nk / (nzc * 2) >= 32) nzc *= 2;
+    // z chunks: every chunk pays a 2V-plane prologue of w (registers only: cheap); aim at several waves of 148 SMs x 3 CTAs, chunks of
+    // at least 6 planes (profiles/r02_theta_march_chunks.log: channel 160x192x192 0.081 -> 0.070 ms with 32 instead of 4 chunks)
+    int nzc = (148 * 3 * 8 + gx * gy - 1) / (gx * gy);
+    nzc = nzc < nk / 6 ? nzc : nk / 6;
+    nzc = nzc < 1 ? 1 : nzc;
+    if (const char *e = getenv("CUDNS_THETA_ZCHUNKS")) { const int n = atoi(e); if (n >= 1 && nk / n >= 2 * kc.v + 1) nzc = n; }   // experiments
     int zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);
