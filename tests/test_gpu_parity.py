@@ -200,6 +200,35 @@ def test_channel_forcing_controller_vs_oracle():
         assert abs(b1[i] - a1[i]) <= 1e-12 * abs(a1[i]) and abs(b2[i] - a2[i]) <= 1e-12 * abs(a2[i])
 
 
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("scheme", ["kutta", "rk4"])
+@pytest.mark.parametrize("name", ["chan_s3v2", "bl_s3v2"])
+def test_walls_and_boundary_layer_with_the_three_register_schemes(name, scheme, prec):
+    """Kutta RK3 and RK4 (base state != input state, second operand, accumulated register: cuda_main.cu:44-107) on the set-ups the
+    lean kernel serves -- the reference's goldens are low-storage runs, so this one is held to the oracle; both precisions"""
+    cfg = dict(CONFIGS[name], lowStorage=0)
+    op = apply_cfg(ob.params_tgv(24, 3), cfg); op.rk4 = int(scheme == "rk4")
+    o = ob.Oracle(op)
+    from common import copy_params
+    cp = copy_params(op, cd.Params()); cp.nranks = 1; cp.rank = 0; cp.device = 0; cp.precision = prec
+    grid = cd.init_grid(cp)
+    s = cd.Solver(cp, grid)
+    g = load_golden(name)
+    if cfg["case"] == "blayer":
+        x, r, u, w, e = blasius_profiles()
+        sx, sz, ref, ic = cd.build_sponge(cp, grid, x[1:], r[1:], u[1:], w[1:])
+        s.set_sponge(sx, sz, ref); o.set_sponge_from_profiles(x[1:], r[1:], u[1:], w[1:], e[1:])   # quirk Q9, as the goldens
+    st = list(g["file0"])
+    o.set_state(st); s.set_state(st)
+    o.run(6); s.advance(6)
+    got = conserved(s.get_state()); ref = conserved(o.state())
+    mom = max(np.abs(ref[k]).max() for k in (1, 2, 3))
+    errs = [relerr(got[0], ref[0])] + [relerr(got[k], ref[k], floor=mom) for k in (1, 2, 3)] + [relerr(got[4], ref[4])]
+    print(name, scheme, "f32" if prec else "f64", ["%.1e" % e for e in errs])
+    assert max(errs) < (3e-6 if prec else 5e-12), errs             # measured: 7e-7 / 2e-15 (profiles/r02_schemes_walls.log)
+    s.close()
+
+
 def test_state_roundtrip_and_errors():
     op = ob.params_tgv(24, 2)
     o, s, grid = make_pair(op)
