@@ -113,7 +113,7 @@ struct cudns_solver {
     bool aux_valid[3];           // H, T of state[b] (ghosts included) match its (rho,u,v,w,rho*E)
     bool duo;                    // the fifth-generation kernel (stage_duo.inc) serves EVERY stage of this configuration (CUDNS_DUO=0: off)
     DuoMaps dmaps[3];            // its TMA descriptors per state buffer
-    bool theta_tma;              // the dilatation pass runs its TMA variant (periodic / uniform set-ups, even mx; CUDNS_THETA_TMA=0: off)
+    bool theta_tma;              // the dilatation pass runs its TMA variant (even mx; CUDNS_THETA_TMA=0: the cp.async variant)
     ThetaMaps tmaps[3];          // u, v, w boxes of every state buffer
 };
 
@@ -335,7 +335,7 @@ int cudns_create(const cudns_params *p, const double *x, const double *xp, const
         }
         {
             const char *te = getenv("CUDNS_THETA_TMA");
-            S->theta_tma = p->periodicX && !p->nonUniformX && !p->boundaryLayer && mx % 2 == 0 && !(te && std::string(te) == "0") &&
+            S->theta_tma = mx % 2 == 0 && !(te && std::string(te) == "0") &&
                            (size_t)theta_tma_smem_bytes(v) <= prop.sharedMemPerBlockOptin;
             for (int b = 0; S->theta_tma && b < S->nstate; b++) {
                 real *q = S->state[b];

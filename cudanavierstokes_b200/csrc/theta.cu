@@ -223,7 +223,11 @@ template <int V> struct ThCfg {
     static_assert((SU * sizeof(real)) % 128 == 0 && (SV * sizeof(real)) % 128 == 0 && (SW * sizeof(real)) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-template <int V>
+// GEN adds what the wall-bounded set-ups need (BCxderVel boundary_condition_x.h:38-40,67,94; BCzderVel boundary_condition_z.h:34-40):
+// the ghost columns of u at a wall / the free stream are rebuilt in the landed plane by the warp that owns the row (they depend on
+// that row only), du/dx carries the metric xp, and the planes next to the global z ends of the boundary layer take the slow
+// extrapolating dw/dz; planes outside the global z range are skipped (the stage kernel extrapolates theta there itself)
+template <int V, bool GEN>
 __global__ void __launch_bounds__(TH_NT, 2)
 theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, const real *__restrict__ wfield, int zchunk,
                  const __grid_constant__ ThetaMaps tm) {
@@ -239,6 +243,12 @@ theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, con
     const int kfirst = -V + (int)blockIdx.z * zchunk;
     const int klast = min(kfirst + zchunk, L.mz + V);                             // exclusive
     const uint32_t mb0 = th_smem_u32(mbar_p), s0 = th_smem_u32(sth);
+    const bool perx = !GEN || c.periodicX != 0, bl = GEN && c.boundaryLayer != 0;
+    const bool xlo = !perx && i0 == 0, xhi = !perx && (i0 + TH_TX >= L.mx);
+    const int nxt = min(TH_TX, L.mx - i0);
+    const int kglob_lo = -c.kstart, kglob_hi = c.mz_tot - c.kstart;
+    real xp0 = RC(1.0), xp1 = RC(1.0);
+    if constexpr (GEN) { if (c.nonUniformX) { xp0 = c.xp[min(i, L.mx - 1)]; xp1 = c.xp[min(i + 1, L.mx - 1)]; } }
     if (tid == 0) {
         for (int n = 0; n < TH_NS; n++) { th_mbar_init(mb0 + 8 * n, 1); cnt[n] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -267,7 +277,29 @@ theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, con
     int st = 0; uint32_t par = 0;
     for (int k = kfirst; k < klast; k++) {
         th_mbar_wait(mb0 + 8 * st, par);
-        const real *su = sth + (size_t)st * G::STAGE, *sv = su + G::SU, *sw = sv + G::SV;
+        real *su = sth + (size_t)st * G::STAGE;
+        const real *sv = su + G::SU, *sw = sv + G::SV;
+        const bool outside = bl && (k < kglob_lo || k >= kglob_hi);
+        if constexpr (GEN) {
+            if ((xlo || xhi) && !outside && lane < 2 * V) {
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    real *row = su + (ty + 8 * r) * TH_UX;
+                    if (lane < V) {
+                        if (xlo) {
+                            const int gq = V - lane;                          // ghost -gq
+                            real val = -row[GX + gq - 1], pv2;
+                            if (bl && c.perturbed && perturb_theta(c, j0 + ty + 8 * r, k + c.kstart, pv2)) val = pv2;
+                            row[GX - gq] = val;
+                        }
+                    } else if (xhi) {
+                        const int gq = lane - V + 1, last = GX + nxt - 1;
+                        row[last + gq] = bl ? RC(2.0) * row[last] - row[last - gq] : -row[last - gq + 1];
+                    }
+                }
+            }
+            if (xlo || xhi) __syncwarp();
+        }
         real2 th[2];
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -292,7 +324,15 @@ theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, con
                 dwdz0 = fma(c.c1[2][l], wr[r][V + l].x - wr[r][V - l].x, dwdz0);
                 dwdz1 = fma(c.c1[2][l], wr[r][V + l].y - wr[r][V - l].y, dwdz1);
             }
-            th[r] = make_real2((dudx0 + dvdy0) + dwdz0, (dudx1 + dvdy1) + dwdz1);
+            if constexpr (GEN) {
+                if (bl && act[r] && !outside && (k - kglob_lo < V || kglob_hi - 1 - k < V)) {
+                    dwdz0 = dwdz_edge<V>(c, wfield, i, j0 + row, k, kglob_lo, kglob_hi);
+                    dwdz1 = dwdz_edge<V>(c, wfield, i + 1, j0 + row, k, kglob_lo, kglob_hi);
+                }
+                th[r] = make_real2(fma(dudx0, xp0, dvdy0) + dwdz0, fma(dudx1, xp1, dvdy1) + dwdz1);
+            } else {
+                th[r] = make_real2((dudx0 + dvdy0) + dwdz0, (dudx1 + dvdy1) + dwdz1);
+            }
         }
         // this warp is done with the stage: the last of the eight refills it with plane k + TH_NS
         __syncwarp();
@@ -306,16 +346,18 @@ theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, con
         // theta and its periodic images (perBCx / perBCy, boundary.h:38-46): rows as 128-bit stores, x images point by point
 #pragma unroll
         for (int r = 0; r < 2; r++) {
-            if (!act[r]) continue;
+            if (!act[r] || outside) continue;
             const int j = j0 + ty + 8 * r;
             real *pt = theta + L.idx(i, j, k);
             th_stg2(pt, th[r].x, th[r].y);
             if (j < V) th_stg2(pt + (size_t)L.my * L.px, th[r].x, th[r].y);
             if (j >= L.my - V) th_stg2(pt - (size_t)L.my * L.px, th[r].x, th[r].y);
-            if (i < V) pt[L.mx] = th[r].x;
-            if (i + 1 < V) pt[L.mx + 1] = th[r].y;
-            if (i >= L.mx - V) pt[-(ptrdiff_t)L.mx] = th[r].x;
-            if (i + 1 >= L.mx - V) pt[1 - (ptrdiff_t)L.mx] = th[r].y;
+            if (perx) {
+                if (i < V) pt[L.mx] = th[r].x;
+                if (i + 1 < V) pt[L.mx + 1] = th[r].y;
+                if (i >= L.mx - V) pt[-(ptrdiff_t)L.mx] = th[r].x;
+                if (i + 1 >= L.mx - V) pt[1 - (ptrdiff_t)L.mx] = th[r].y;
+            }
         }
         if (++st == TH_NS) { st = 0; par ^= 1u; }
     }
@@ -326,22 +368,29 @@ theta_tma_kernel(const __grid_constant__ KConst c, real *__restrict__ theta, con
 int theta_tma_smem_bytes(int v) {
     switch (v) { case 1: return (int)ThCfg<1>::bytes; case 2: return (int)ThCfg<2>::bytes; case 3: return (int)ThCfg<3>::bytes; default: return (int)ThCfg<4>::bytes; }
 }
-// periodic x, uniform grid, no boundary layer, even mx; q = the padded state whose fields 1..3 the descriptors of `maps` describe
+// even mx; q = the padded state whose fields 1..3 the descriptors of `maps` describe
 void launch_theta_tma(const KConst &kc, const real *q, real *theta, const ThetaMaps &maps, cudaStream_t st) {
     const int gx = (kc.L.mx + TH_TX - 1) / TH_TX, gy = (kc.L.my + TH_TY - 1) / TH_TY;
     const int nk = kc.L.mz + 2 * kc.v;
     // z chunks: every chunk re-reads 2V planes of w; whole waves of 148 SMs x 2 CTAs (512^3: 8 chunks = 6.9 waves, 0.70 ms; the 4
     // chunks = 3.5 waves of the first version: 0.74 ms, profiles/r02_zchunk_sweep.log)
-    int nzc = pick_zchunks(gx * gy, nk, kc.v, 148 * 2, 64);
+    // (grids with fewer tiles than SMs -- the wall-bounded cases -- need short chunks to fill the machine at all)
+    int nzc = pick_zchunks(gx * gy, nk, kc.v, 148 * 2, gx * gy >= 148 ? 64 : 8);
     if (const char *e = getenv("CUDNS_THETA_ZCHUNKS")) { const int n = atoi(e); if (n >= 1 && nk / n >= 8) nzc = n; }      // experiments
     int zchunk = (nk + nzc - 1) / nzc;
     nzc = (nk + zchunk - 1) / zchunk;
     dim3 grid(gx, gy, nzc);
     const real *w = q + 3 * kc.L.vol;
+    const bool gen = !(kc.periodicX && !kc.nonUniformX && !kc.boundaryLayer);
 #define CUDNS_THETA_TMA_CASE(VV)                                                                    \
     {                                                                                               \
-        opt_in_smem<theta_tma_kernel<VV>>((int)ThCfg<VV>::bytes);                                   \
-        theta_tma_kernel<VV><<<grid, TH_NT, ThCfg<VV>::bytes, st>>>(kc, theta, w, zchunk, maps);     \
+        if (gen) {                                                                                  \
+            opt_in_smem<theta_tma_kernel<VV, true>>((int)ThCfg<VV>::bytes);                         \
+            theta_tma_kernel<VV, true><<<grid, TH_NT, ThCfg<VV>::bytes, st>>>(kc, theta, w, zchunk, maps);   \
+        } else {                                                                                    \
+            opt_in_smem<theta_tma_kernel<VV, false>>((int)ThCfg<VV>::bytes);                        \
+            theta_tma_kernel<VV, false><<<grid, TH_NT, ThCfg<VV>::bytes, st>>>(kc, theta, w, zchunk, maps);  \
+        }                                                                                           \
     }
     switch (kc.v) {
         case 1: CUDNS_THETA_TMA_CASE(1) break;
