@@ -224,7 +224,10 @@ bool rhs_stage_supported(int s, int v);
 // time of tail otherwise (wall tiles, unequal clocks).  Fitted to a sweep on one B200 (profiles/r02_zchunk_sweep.log: channel
 // 160x192x192 0.59 -> 0.53 ms per stage, boundary layer and Taylor-Green 512^3 unchanged within 1.5 %).  Any n is allowed, not only
 // powers of two; chunks stay >= 16 planes (the bandwidth-bound dilatation pass: >= 64, its tail wave costs less).
-inline int pick_zchunks(int cols, int mz, int s, int resident, int min_chunk = 16) {
+// whole_waves: weigh the count of whole waves and the w + 1 rule equally -- the wall-bounded set-ups of the lean kernel, whose CTAs
+// take nearly equal times (profiles/r02_channel_stage_chunks.log: channel 160x192x192, 80 tiles: 9 or 11 chunks = 4.9 / 5.9 waves
+// 0.411 ms, 12 chunks = 6.5 waves 0.431 ms)
+inline int pick_zchunks(int cols, int mz, int s, int resident, int min_chunk = 16, bool whole_waves = false) {
     if (const char *e = getenv("CUDNS_ZCHUNKS")) { const int n = atoi(e); if (n >= 1 && mz / n >= 2 * s + 1) return n; }   // experiments
     int best = 1; double best_cost = 1e300;
     for (int n = 1; n <= 128; n++) {
@@ -233,7 +236,8 @@ inline int pick_zchunks(int cols, int mz, int s, int resident, int min_chunk = 1
         const int nn = (mz + zc - 1) / zc;                         // chunks this plane count really gives
         const long ctas = (long)cols * nn;
         const double w = (double)ctas / resident, waves = (double)((ctas + resident - 1) / resident);
-        const double cost = (waves > w + 1.0 ? waves : w + 1.0) * (zc + 0.8 * s);
+        const double tail = waves > w + 1.0 ? waves : w + 1.0;
+        const double cost = (whole_waves ? 0.5 * waves + 0.5 * (w + 1.0) : tail) * (zc + 0.8 * s);
         if (cost < best_cost * 0.995) { best_cost = cost; best = nn; }
     }
     return best;

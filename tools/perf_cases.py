@@ -1,6 +1,6 @@
 """Throughput of the non-periodic BASELINE configurations at their full sizes (the lean GEN stage kernel):
 C3 supersonic isothermal channel 160x192x192 (4th order: s=v=2, and the preset's s=3,v=2), C4 boundary layer 240x64x2048
-with sponges and wall blowing/suction (s=3,v=2).  usage: tools/perf_cases.py [steps] [f32]"""
+with sponges and wall blowing/suction (s=3,v=2).  usage: tools/perf_cases.py [steps] [f32|f64] [name filter]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,8 +10,11 @@ from ref_cases import CONFIGS, apply_cfg, blasius_profiles
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 prec = int(len(sys.argv) > 2 and sys.argv[2] == "f32")
+only = sys.argv[3] if len(sys.argv) > 3 else ""
 
 def run(name, cfg, over):
+    if only not in name:
+        return
     p = apply_cfg(cd.Params(), dict(cfg, **over)); p.gam = 1.4; p.TwallTop = p.TwallBot = 1.0; p.quirk_q1 = 1; p.nranks = 1; p.precision = prec
     ref = cd.params_blayer() if cfg["case"] == "blayer" else cd.params_channel()
     for k in ("spTopStr", "spTopLen", "spTopExp", "spInlStr", "spInlLen", "spInlExp", "spOutStr", "spOutLen", "spOutExp",
